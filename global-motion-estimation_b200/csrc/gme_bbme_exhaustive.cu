@@ -1,0 +1,279 @@
+// gme_bbme_exhaustive.cu -- exhaustive block matching (K1), the integer-pipe-bound kernel.
+//
+// Replaces bbme.exhaustive_search (bbme.py:105-179).  One CTA owns NB horizontally adjacent
+// macroblocks of one block row.  The search window of the CURRENT frame
+// (2*sw + 2*bs - 1 rows) is staged in shared memory by one TMA box load; candidates that
+// fall outside the frame are skipped by predicate exactly like bbme.py:157-162 (TMA's
+// zero fill is never used as data).  A thread owns one COLUMN offset of one macroblock and
+// walks down the window: each window row is loaded once (WPR+1 words, funnel-shifted to
+// the thread's byte alignment) and scored against all BS anchor rows held in registers,
+// feeding BS rotating accumulators -- one candidate (row offset) completes per window row.
+// Inner loop: 1 LDS per ~13 VABSDIFF4.ACC (SAD) or VABSDIFF4+IDP.4A pairs (SSD).
+//
+// Tie-breaking: the reference scans column offset outer, row offset inner and keeps the first
+// strict minimum (bbme.py:146-174).  A thread sees its row offsets in ascending order (strict
+// '<'), threads are merged by a 64-bit key (cost, column index, row index) with atomicMin.
+#include "gme_common.cuh"
+
+namespace gme {
+
+struct ExhaustiveArgs {
+    const uint8_t *prev;
+    size_t prev_stride;
+    const uint8_t *cur;
+    size_t cur_stride;
+    int H, W;
+    size_t pitch;
+    int R, C;
+    int sw;
+    int32_t *field;
+    int nb;             // macroblocks per CTA
+    int tpb;            // threads per macroblock (<= ncand)
+    int win_w, win_h;   // staged window (bytes per row, rows)
+    int use_tma;
+};
+
+template <int BS, int PNORM, int NT>
+__global__ void __launch_bounds__(NT) bbme_exhaustive_kernel(const __grid_constant__ CUtensorMap cur_map,
+                                                             ExhaustiveArgs a)
+{
+    constexpr int WPR = (BS + 3) / 4;
+    constexpr uint32_t LAST_MASK = (BS % 4 == 0) ? 0xFFFFFFFFu : ((1u << (8 * (BS % 4))) - 1u);
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+
+    const int plane = blockIdx.z, bi = blockIdx.y, bj0 = blockIdx.x * a.nb;
+    const int br = bi * BS, bc0 = bj0 * BS;
+    const int ncand = 2 * a.sw + BS;                 // offsets per axis: [-sw, sw+bs-1]  (bbme.py:146-149)
+    const int wr0 = br - a.sw, wc0 = bc0 - a.sw;     // image coordinates of window (0, 0)
+    const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
+    const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
+
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem);
+    const int win_pw = a.win_w / 4;
+    const size_t win_bytes = ((size_t)a.win_w * a.win_h + 32 + 127) / 128 * 128;
+    uint32_t *anchors = reinterpret_cast<uint32_t *>(smem + win_bytes);                    // [nb][BS][WPR]
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(anchors + a.nb * BS * WPR + (a.nb * BS * WPR & 1));
+
+    // ---- stage the window (TMA) and the anchor blocks ------------------------------------
+    if (a.use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&bar, (uint32_t)(a.win_w * a.win_h));
+            tma_load_3d(smem, &cur_map, &bar, wc0, wr0, plane);
+        }
+    } else {
+        for (int i = threadIdx.x; i < win_pw * a.win_h; i += NT) {
+            const int rr = wr0 + i / win_pw, cc = wc0 + (i % win_pw) * 4;
+            uint32_t v = 0;
+            if (rr >= 0 && rr < a.H) {
+                const uint8_t *p = cur_plane + (size_t)rr * a.pitch;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (cc + k >= 0 && cc + k < a.W) v |= (uint32_t)p[cc + k] << (8 * k);
+            }
+            win[i] = v;
+        }
+    }
+    for (int i = threadIdx.x; i < a.nb * BS * WPR; i += NT) {
+        const int b = i / (BS * WPR), r = (i / WPR) % BS, w = i % WPR;
+        uint32_t v = 0;
+        if (bj0 + b < a.C) {
+            const uint8_t *p = prev_plane + (size_t)(br + r) * a.pitch + (bc0 + b * BS) + 4 * w;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (4 * w + k < BS) v |= (uint32_t)p[k] << (8 * k);
+        }
+        anchors[i] = v;
+    }
+    for (int i = threadIdx.x; i < a.nb; i += NT) keys[i] = ~0ull;
+    __syncthreads();
+    if (a.use_tma) mbar_wait(&bar, 0);
+
+    // ---- per-thread search ------------------------------------------------------------------
+    const int b = threadIdx.x / a.tpb, t_in = threadIdx.x % a.tpb;
+    if (b < a.nb && bj0 + b < a.C) {
+        uint32_t anc[BS][WPR];
+#pragma unroll
+        for (int r = 0; r < BS; r++)
+#pragma unroll
+            for (int w = 0; w < WPR; w++) anc[r][w] = anchors[(b * BS + r) * WPR + w];
+
+        const int bc = bc0 + b * BS;
+        // row offsets j (wr = j - sw) whose candidate is inside the frame: 0 <= br + wr <= H - BS
+        const int jlo = max(0, a.sw - br), jhi = min(ncand - 1, a.H - BS - br + a.sw);
+        unsigned long long best_key = ~0ull;
+        for (int ci = t_in; ci < ncand; ci += a.tpb) {
+            const int left = bc + ci - a.sw;
+            if (left < 0 || left > a.W - BS) continue;          // bbme.py:157-162, column part
+            const int x0 = b * BS + ci;                          // byte column inside the window
+            const int sh = (x0 & 3) * 8;
+            const uint32_t *wp = win + (x0 >> 2);
+            uint32_t acc[BS];
+#pragma unroll
+            for (int s = 0; s < BS; s++) acc[s] = 0;
+            uint32_t best = 0xFFFFFFFFu;
+            int bestj = 0;
+            for (int y0 = 0; y0 < a.win_h; y0 += BS) {
+#pragma unroll
+                for (int yy = 0; yy < BS; yy++) {
+                    const int y = y0 + yy;
+                    if (y < a.win_h) {
+                        const uint32_t *row = wp + y * win_pw;
+                        uint32_t raw[WPR + 1], w[WPR];
+#pragma unroll
+                        for (int i = 0; i <= WPR; i++) raw[i] = row[i];
+#pragma unroll
+                        for (int i = 0; i < WPR; i++) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+                        w[WPR - 1] &= LAST_MASK;
+#pragma unroll
+                        for (int k = 0; k < BS; k++) {           // window row y is row k of candidate j = y - k
+                            const int s = (yy - k + BS) % BS;
+#pragma unroll
+                            for (int i = 0; i < WPR; i++) acc[s] = cost4_acc<PNORM>(w[i], anc[k][i], acc[s]);
+                        }
+                        const int sdone = (yy + 1) % BS;         // candidate j = y - BS + 1 is complete
+                        const int j = y - BS + 1;
+                        if (j >= jlo && j <= jhi && acc[sdone] < best) { best = acc[sdone]; bestj = j; }
+                        acc[sdone] = 0;
+                    }
+                }
+            }
+            if (best != 0xFFFFFFFFu) {
+                const unsigned long long key =
+                    ((unsigned long long)best << 32) | ((unsigned long long)ci << 16) | (unsigned long long)bestj;
+                best_key = key < best_key ? key : best_key;
+            }
+        }
+        if (best_key != ~0ull) atomicMin(&keys[b], best_key);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.nb; i += NT) {
+        if (bj0 + i < a.C) {
+            const unsigned long long key = keys[i];
+            const int ci = (int)((key >> 16) & 0xFFFF), j = (int)(key & 0xFFFF);
+            int32_t *f = a.field + (((size_t)plane * a.R + bi) * a.C + bj0 + i) * 2;
+            f[0] = ci - a.sw;      // column offset -> channel 0 (bbme.py:176)
+            f[1] = j - a.sw;       // row offset    -> channel 1 (bbme.py:177)
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic path: any block size / window, a warp per macroblock, lanes over candidates.
+// ---------------------------------------------------------------------------------------
+template <int PNORM>
+__global__ void __launch_bounds__(256) bbme_exhaustive_generic_kernel(ExhaustiveArgs a, int bs)
+{
+    const int plane = blockIdx.z;
+    const long nblocks = (long)a.R * a.C;
+    const long b = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (b >= nblocks) return;
+    const int lane = threadIdx.x & 31;
+    const int bi = (int)(b / a.C), bj = (int)(b % a.C), br = bi * bs, bc = bj * bs;
+    const uint8_t *anchor = a.prev + (size_t)plane * a.prev_stride + (size_t)br * a.pitch + bc;
+    const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
+    const int ncand = 2 * a.sw + bs;
+    unsigned long long best_key = ~0ull;
+    for (long idx = lane; idx < (long)ncand * ncand; idx += 32) {      // idx = ci * ncand + j: the scan order
+        const int ci = (int)(idx / ncand), j = (int)(idx % ncand);
+        const int top = br + j - a.sw, left = bc + ci - a.sw;
+        if (top < 0 || left < 0 || top + bs > a.H || left + bs > a.W) continue;
+        const uint8_t *cand = cur_plane + (size_t)top * a.pitch + left;
+        uint32_t acc = 0;
+        for (int r = 0; r < bs; r++)
+            for (int c = 0; c < bs; c++) {
+                const int d = (int)anchor[(size_t)r * a.pitch + c] - (int)cand[(size_t)r * a.pitch + c];
+                acc += (PNORM == GME_PNORM_MAE) ? (uint32_t)abs(d) : (uint32_t)(d * d);
+            }
+        const unsigned long long key = ((unsigned long long)acc << 32) | (unsigned long long)idx;
+        best_key = key < best_key ? key : best_key;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best_key, o);
+        best_key = other < best_key ? other : best_key;
+    }
+    if (lane == 0) {
+        const long idx = (long)(best_key & 0xFFFFFFFFull);
+        int32_t *f = a.field + ((size_t)plane * nblocks + b) * 2;
+        f[0] = (int)(idx / ncand) - a.sw;
+        f[1] = (int)(idx % ncand) - a.sw;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host launcher
+// ---------------------------------------------------------------------------------------
+template <int BS, int PNORM>
+static int launch_fast(ExhaustiveArgs a, int n, cudaStream_t stream, bool *handled)
+{
+    constexpr int NT = 384;
+    constexpr int WPR = (BS + 3) / 4;
+    const int ncand = 2 * a.sw + BS;
+    *handled = false;
+    if (ncand > 0xFFFF) return GME_OK;
+    int tpb = min(ncand, NT);
+    int nb = max(1, min(NT / tpb, a.C));
+    const int win_h = 2 * a.sw + 2 * BS - 1;
+    int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4;       // +4: trailing word of the funnel shift
+    win_w = (win_w + 15) / 16 * 16;
+    const size_t win_bytes = ((size_t)win_w * win_h + 32 + 127) / 128 * 128;
+    const size_t smem = win_bytes + (size_t)(nb * BS * WPR + 1) * 4 + (size_t)nb * 8 + 16;
+    if (smem > 200 * 1024) return GME_OK;                        // window too large for shared memory: generic path
+    a.nb = nb; a.tpb = tpb; a.win_w = win_w; a.win_h = win_h;
+    CUtensorMap map;
+    a.use_tma = (win_w <= 256 && win_h <= 256 &&
+                 make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h)) ? 1 : 0;
+    if (!a.use_tma) memset(&map, 0, sizeof(map));
+    auto kern = bbme_exhaustive_kernel<BS, PNORM, NT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((a.C + nb - 1) / nb, a.R, n);
+    kern<<<grid, NT, smem, stream>>>(map, a);
+    note_launch();
+    *handled = true;
+    return check_launch("bbme_exhaustive_kernel");
+}
+
+template <int PNORM>
+static int launch_exhaustive_pn(ExhaustiveArgs a, int n, int bs, cudaStream_t stream)
+{
+    bool handled = false;
+    int rc = GME_OK;
+    switch (bs) {
+    case 2: rc = launch_fast<2, PNORM>(a, n, stream, &handled); break;
+    case 4: rc = launch_fast<4, PNORM>(a, n, stream, &handled); break;
+    case 8: rc = launch_fast<8, PNORM>(a, n, stream, &handled); break;
+    case 12: rc = launch_fast<12, PNORM>(a, n, stream, &handled); break;
+    case 16: rc = launch_fast<16, PNORM>(a, n, stream, &handled); break;
+    default: break;
+    }
+    if (handled || rc != GME_OK) return rc;
+    const long nblocks = (long)a.R * a.C;
+    const int warps = 8;
+    dim3 grid((unsigned)((nblocks + warps - 1) / warps), 1, n);
+    bbme_exhaustive_generic_kernel<PNORM><<<grid, warps * 32, 0, stream>>>(a, bs);
+    note_launch();
+    return check_launch("bbme_exhaustive_generic_kernel");
+}
+
+int launch_bbme_exhaustive(const uint8_t *prev, size_t prev_stride, const uint8_t *cur, size_t cur_stride, int n,
+                           int H, int W, size_t pitch, int bs, int sw, int pnorm, int32_t *field, cudaStream_t stream)
+{
+    ExhaustiveArgs a{};
+    a.prev = prev; a.prev_stride = prev_stride;
+    a.cur = cur; a.cur_stride = cur_stride;
+    a.H = H; a.W = W; a.pitch = pitch;
+    a.R = H / bs; a.C = W / bs;
+    a.sw = sw;
+    a.field = field;
+    if (a.R == 0 || a.C == 0 || n == 0) return GME_OK;
+    return pnorm == GME_PNORM_MAE ? launch_exhaustive_pn<GME_PNORM_MAE>(a, n, bs, stream)
+                                  : launch_exhaustive_pn<GME_PNORM_MSE>(a, n, bs, stream);
+}
+
+}  // namespace gme

@@ -1,0 +1,513 @@
+// gme_bbme_pattern.cu -- three-step, 2D-log and diamond block matching (K2).
+//
+// Replaces bbme.threestep_search (bbme.py:182-341), bbme.twodlog_search (bbme.py:344-433)
+// and bbme.diamond_search (bbme.py:436-534).  One CTA owns a tile of macroblocks; the part
+// of the CURRENT frame the tile can plausibly reach (tile + margin) is staged in shared
+// memory by one TMA box load (cooperative loads when the planes are not TMA-aligned).  A
+// group of G lanes owns one macroblock: every lane keeps its share of the anchor block in
+// registers, evaluates its share of each candidate with packed byte ops (VABSDIFF4 /
+// IDP.4A) and the group sums with warp shuffles.  The walk of the search is data
+// dependent and unbounded in the reference, so a candidate that leaves the staged window
+// is evaluated straight from global memory -- same integers, only slower.
+//
+// Scan orders, strict '<' first-minimum tie-breaking, the diamond clamp to H-bs-1, the
+// swapped SDSP offsets, the double-counted three-step offset and the unbounded 2D-log walk
+// are reproduced exactly; the oracle is oracle/gme_oracle.c.
+#include "gme_common.cuh"
+
+namespace gme {
+
+struct PatternArgs {
+    const uint8_t *prev;
+    size_t prev_stride;
+    const uint8_t *cur;
+    size_t cur_stride;
+    int H, W;
+    size_t pitch;
+    int R, C;          // macroblocks per frame
+    int sw, procedure;
+    int32_t *field;    // [n][R][C][2]
+    int tbx, tby;      // macroblocks per tile
+    int margin;        // staged margin around the tile, pixels
+    int win_w, win_h;  // staged window: win_w bytes per row (multiple of 16), win_h rows
+    int use_tma;
+};
+
+constexpr uint32_t kInfCost = 0xFFFFFFFFu;   // every real cost is < 2^32 - 1 (bs <= 255 checked on the host)
+
+// ---------------------------------------------------------------------------------------
+// Fast path: compile-time block size, G lanes per macroblock, window in shared memory.
+// ---------------------------------------------------------------------------------------
+template <int BS, int G, int PNORM>
+struct BlockEval {
+    static constexpr int WPR = (BS + 3) / 4;          // 32-bit words per block row
+    static constexpr int UNITS = BS * WPR;            // words per block
+    static constexpr int UPL = (UNITS + G - 1) / G;   // words per lane
+
+    uint32_t anchor[UPL];
+    const uint8_t *cur_plane;
+    const uint32_t *win;      // shared window
+    size_t pitch;
+    int win_pw;               // window pitch in words
+    int wr0, wc0, wr1, wc1;   // window covers rows [wr0, wr1) and columns [wc0, wc1)
+    int lane_g;               // lane index inside the group
+    uint32_t gmask;           // shuffle mask of the group
+
+    __device__ __forceinline__ void load_anchor(const uint8_t *prev_plane, int br, int bc)
+    {
+#pragma unroll
+        for (int t = 0; t < UPL; t++) {
+            const int u = lane_g + t * G;
+            uint32_t v = 0;
+            if (u < UNITS) {
+                const int ur = u / WPR, uw = u % WPR;
+                const uint8_t *p = prev_plane + (size_t)(br + ur) * pitch + bc + 4 * uw;
+                const int nv = min(4, BS - 4 * uw);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < nv) v |= (uint32_t)p[k] << (8 * k);
+            }
+            anchor[t] = v;
+        }
+    }
+
+    __device__ __forceinline__ bool inside(int r, int c) const
+    {
+        return r >= wr0 && r + BS <= wr1 && c >= wc0 && c + BS <= wc1;
+    }
+
+    // this lane's share of the cost of the candidate whose top-left pixel is (r, c)
+    __device__ __forceinline__ uint32_t partial_smem(int r, int c) const
+    {
+        uint32_t acc = 0;
+        const int x0 = c - wc0;
+        const int sh = (x0 & 3) * 8;
+        const uint32_t *base = win + (r - wr0) * win_pw + (x0 >> 2);
+#pragma unroll
+        for (int t = 0; t < UPL; t++) {
+            const int u = lane_g + t * G;
+            if (UNITS % G == 0 || u < UNITS) {
+                const int ur = u / WPR, uw = u % WPR;
+                const uint32_t *p = base + ur * win_pw + uw;
+                uint32_t v = __funnelshift_r(p[0], p[1], sh);
+                if (BS % 4 != 0 && uw == WPR - 1) v &= byte_mask(BS - 4 * (WPR - 1));
+                acc = cost4_acc<PNORM>(v, anchor[t], acc);
+            }
+        }
+        return acc;
+    }
+
+    __device__ __forceinline__ uint32_t partial_gmem(int r, int c) const
+    {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int t = 0; t < UPL; t++) {
+            const int u = lane_g + t * G;
+            if (UNITS % G == 0 || u < UNITS) {
+                const int ur = u / WPR, uw = u % WPR;
+                const int nv = min(4, BS - 4 * uw);
+                const size_t off = (size_t)(r + ur) * pitch + (size_t)(c + 4 * uw);
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(cur_plane + (off & ~(size_t)3));
+                const int mis = (int)(off & 3);
+                const uint32_t lo = __ldg(p);
+                const uint32_t hi = (mis + nv > 4) ? __ldg(p + 1) : 0u;   // never touch a word with no valid byte
+                uint32_t v = __funnelshift_r(lo, hi, mis * 8);
+                v &= byte_mask(nv);
+                acc = cost4_acc<PNORM>(v, anchor[t], acc);
+            }
+        }
+        return acc;
+    }
+
+    __device__ __forceinline__ uint32_t reduce(uint32_t v) const
+    {
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    }
+
+    // costs of N candidates; all loads are issued before the reductions (ILP)
+    template <int N>
+    __device__ __forceinline__ void eval(const int (&r)[N], const int (&c)[N], uint32_t (&cost)[N]) const
+    {
+        bool all_in = true;
+#pragma unroll
+        for (int k = 0; k < N; k++) all_in &= inside(r[k], c[k]);
+        uint32_t part[N];
+        if (all_in) {
+#pragma unroll
+            for (int k = 0; k < N; k++) part[k] = partial_smem(r[k], c[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; k++) part[k] = partial_gmem(r[k], c[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) cost[k] = reduce(part[k]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// The three searches, written once over any evaluator E (fast or generic).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cand_in_frame(int top, int left, int bs, int H, int W)
+{
+    // bbme.py:239-244, 405-411
+    return !(top < 0 || left < 0 || top + bs - 1 > H - 1 || left + bs - 1 > W - 1);
+}
+
+template <class E>
+__device__ __forceinline__ void diamond_walk(const E &e, int bs, int H, int W, int br, int bc, int &out0, int &out1)
+{
+    // LDSP / SDSP offsets as (row, col): bbme.py:463-480; the SDSP list is applied swapped (bbme.py:518-521)
+    constexpr int LR[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};
+    constexpr int LC[9] = {0, 0, 1, 2, 1, 0, -1, -2, -1};
+    constexpr int SR[5] = {0, 0, 1, 0, -1};
+    constexpr int SC[5] = {0, 1, 0, -1, 0};
+    const int rmax = H - bs - 1, cmax = W - bs - 1;   // bbme.py:503-504 (off by one, kept)
+    int mr = br, mc = bc;
+    bool stop = false;
+    while (!stop) {                                   // bbme.py:494-513
+        int r[9], c[9];
+        uint32_t cost[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            r[k] = clampi(mr + LR[k], 0, rmax);
+            c[k] = clampi(mc + LC[k], 0, cmax);
+        }
+        e.template eval<9>(r, c, cost);
+        uint32_t best = kInfCost;
+        int best_r = mr, best_c = mc;
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = c[k]; }
+        stop = (best_r == mr) && (best_c == mc);
+        mr = best_r;
+        mc = best_c;
+    }
+    int r[5], c[5];
+    uint32_t cost[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        r[k] = clampi(mr + SR[k], 0, rmax);
+        c[k] = clampi(mc + SC[k], 0, cmax);
+    }
+    e.template eval<5>(r, c, cost);
+    uint32_t best = kInfCost;
+    int best_r = mr, best_c = mc;
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+        if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = c[k]; }
+    out1 = best_r - br;                               // bbme.py:531-532
+    out0 = best_c - bc;
+}
+
+template <class E>
+__device__ __forceinline__ void threestep_walk(const E &e, int bs, int sw, int H, int W, int br, int bc, int &out0,
+                                               int &out1)
+{
+    const int span = 2 * sw + bs;
+    const int steps[3] = {span / 3, span / 5, span / 10};     // bbme.py:211-213
+    int dx = 0, dy = 0, tmp_dx = 0, tmp_dy = 0;
+    int orow = br, ocol = bc;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+        const int st = steps[s];
+        int r[9], c[9];
+        bool ok[9];
+        uint32_t cost[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {                          // k = 3*ic + ir: column offset outer (bbme.py:229-231)
+            const int offr = (k % 3 - 1) * st, offc = (k / 3 - 1) * st;
+            const int top = orow + offr, left = ocol + offc;
+            ok[k] = cand_in_frame(top, left, bs, H, W);
+            r[k] = ok[k] ? top : br;                           // out-of-frame candidates are skipped, never loaded
+            c[k] = ok[k] ? left : bc;
+        }
+        e.template eval<9>(r, c, cost);
+        uint32_t best = kInfCost;
+        int bx = (s == 0) ? dx : tmp_dx, by = (s == 0) ? dy : tmp_dy;
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            if (ok[k] && cost[k] < best) { best = cost[k]; bx = (k % 3 - 1) * st; by = (k / 3 - 1) * st; }
+        if (s == 0) {
+            dx = bx; dy = by;
+            orow = br + dx; ocol = bc + dy;                    // bbme.py:260-261
+        } else if (s == 1) {
+            tmp_dx = bx; tmp_dy = by;
+            dx += tmp_dx; dy += tmp_dy;                        // bbme.py:296-297
+            orow += dx; ocol += dy;                            // bbme.py:300-301: step-1 offset counted twice
+        } else {
+            tmp_dx = bx; tmp_dy = by;                          // stale step-2 value survives when nothing was in frame
+            dx += tmp_dx; dy += tmp_dy;                        // bbme.py:335-336
+        }
+    }
+    out0 = dy;                                                 // bbme.py:338-339
+    out1 = dx;
+}
+
+template <class E>
+__device__ __forceinline__ void twodlog_walk(const E &e, int bs, int sw, int H, int W, int br, int bc, int &out0,
+                                             int &out1)
+{
+    int dx = 0, dy = 0;                                        // bbme.py:371
+    int x = br, y = bc;
+    int step = sw;
+    while (step > 1) {                                         // bbme.py:381
+        uint32_t best = kInfCost;
+        if (step > 2) {                                        // cross, bbme.py:387-393
+            int r[5] = {x, x + step, x - step, x, x};
+            int c[5] = {y, y, y, y + step, y - step};
+            int pr[5], pc[5];
+            bool ok[5];
+            uint32_t cost[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                ok[k] = cand_in_frame(r[k], c[k], bs, H, W);
+                pr[k] = ok[k] ? r[k] : br;
+                pc[k] = ok[k] ? c[k] : bc;
+            }
+            e.template eval<5>(pr, pc, cost);
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (ok[k] && cost[k] < best) { best = cost[k]; dx = r[k]; dy = c[k]; }
+        } else {                                               // step == 2: 3x3, row outer (bbme.py:394-398)
+            int r[9], c[9], pr[9], pc[9];
+            bool ok[9];
+            uint32_t cost[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                r[k] = x + (k / 3 - 1) * 2;
+                c[k] = y + (k % 3 - 1) * 2;
+                ok[k] = cand_in_frame(r[k], c[k], bs, H, W);
+                pr[k] = ok[k] ? r[k] : br;
+                pc[k] = ok[k] ? c[k] : bc;
+            }
+            e.template eval<9>(pr, pc, cost);
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                if (ok[k] && cost[k] < best) { best = cost[k]; dx = r[k]; dy = c[k]; }
+        }
+        if ((dx == x && dy == y) || step == 2) step /= 2;      // bbme.py:423-425
+        x = dx;
+        y = dy;
+    }
+    out1 = dx - br;                                            // bbme.py:430-431 (-position when the loop never ran)
+    out0 = dy - bc;
+}
+
+template <class E>
+__device__ __forceinline__ void run_search(const E &e, int procedure, int bs, int sw, int H, int W, int br, int bc,
+                                           int &o0, int &o1)
+{
+    if (procedure == GME_SEARCH_DIAMOND)
+        diamond_walk(e, bs, H, W, br, bc, o0, o1);
+    else if (procedure == GME_SEARCH_THREESTEP)
+        threestep_walk(e, bs, sw, H, W, br, bc, o0, o1);
+    else
+        twodlog_walk(e, bs, sw, H, W, br, bc, o0, o1);
+}
+
+// ---------------------------------------------------------------------------------------
+// Window staging shared by the pattern and exhaustive kernels.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_window(uint8_t *smem_win, uint64_t *bar, const CUtensorMap *map, int use_tma,
+                                             const uint8_t *plane, int plane_idx, int H, int W, size_t pitch, int wr0,
+                                             int wc0, int win_w, int win_h)
+{
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(win_w * win_h));
+            tma_load_3d(smem_win, map, bar, wc0, wr0, plane_idx);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        // cooperative loader for planes that are not TMA-aligned: zero-fill outside the frame like TMA does
+        uint32_t *w = reinterpret_cast<uint32_t *>(smem_win);
+        const int pw = win_w / 4;
+        for (int i = threadIdx.x; i < pw * win_h; i += blockDim.x) {
+            const int rr = wr0 + i / pw, cc = wc0 + (i % pw) * 4;
+            uint32_t v = 0;
+            if (rr >= 0 && rr < H) {
+                const uint8_t *p = plane + (size_t)rr * pitch;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (cc + k >= 0 && cc + k < W) v |= (uint32_t)p[cc + k] << (8 * k);
+            }
+            w[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+template <int BS, int G, int PNORM, int NT>
+__global__ void __launch_bounds__(NT) bbme_pattern_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+
+    const int plane = blockIdx.z;
+    const int tile_r = blockIdx.y * a.tby, tile_c = blockIdx.x * a.tbx;   // first macroblock of the tile
+    const int wr0 = tile_r * BS - a.margin, wc0 = tile_c * BS - a.margin;
+    const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
+    const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
+
+    stage_window(smem, &bar, &cur_map, a.use_tma, cur_plane, plane, a.H, a.W, a.pitch, wr0, wc0, a.win_w, a.win_h);
+
+    BlockEval<BS, G, PNORM> e;
+    e.cur_plane = cur_plane;
+    e.win = reinterpret_cast<const uint32_t *>(smem);
+    e.pitch = a.pitch;
+    e.win_pw = a.win_w / 4;
+    e.wr0 = wr0;
+    e.wc0 = wc0;
+    e.wr1 = wr0 + a.win_h;
+    e.wc1 = wc0 + a.win_w - 4;      // the funnel shift reads one word past the block: keep it inside the row
+    const int lane = threadIdx.x & 31;
+    e.lane_g = lane % G;
+    e.gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << (lane - e.lane_g));
+
+    const int group = threadIdx.x / G, ngroups = NT / G;
+    int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
+    for (int b = group; b < a.tbx * a.tby; b += ngroups) {
+        const int bi = tile_r + b / a.tbx, bj = tile_c + b % a.tbx;
+        if (bi >= a.R || bj >= a.C) continue;
+        const int br = bi * BS, bc = bj * BS;
+        e.load_anchor(prev_plane, br, bc);
+        int o0, o1;
+        run_search(e, a.procedure, BS, a.sw, a.H, a.W, br, bc, o0, o1);
+        if (e.lane_g == 0) {
+            int2 v = make_int2(o0, o1);
+            *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic path: any block size 1..255, a full warp per macroblock, global memory only.
+// ---------------------------------------------------------------------------------------
+template <int PNORM>
+struct GenericEval {
+    const uint8_t *prev_block;   // anchor, top-left pixel
+    const uint8_t *cur_plane;
+    size_t pitch;
+    int bs, lane;
+
+    template <int N>
+    __device__ __forceinline__ void eval(const int (&r)[N], const int (&c)[N], uint32_t (&cost)[N]) const
+    {
+        const int npix = bs * bs;
+#pragma unroll 1
+        for (int k = 0; k < N; k++) {
+            const uint8_t *cand = cur_plane + (size_t)r[k] * pitch + c[k];
+            uint32_t acc = 0;
+            for (int p = lane; p < npix; p += 32) {
+                const int pr = p / bs, pc = p - pr * bs;
+                const int d = (int)prev_block[(size_t)pr * pitch + pc] - (int)cand[(size_t)pr * pitch + pc];
+                acc += (PNORM == GME_PNORM_MAE) ? (uint32_t)abs(d) : (uint32_t)(d * d);
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+            cost[k] = acc;
+        }
+    }
+};
+
+template <int PNORM>
+__global__ void __launch_bounds__(256) bbme_pattern_generic_kernel(PatternArgs a, int bs)
+{
+    const int plane = blockIdx.z;
+    const int warps_per_cta = blockDim.x / 32;
+    const long nblocks = (long)a.R * a.C;
+    const long b = (long)blockIdx.x * warps_per_cta + threadIdx.x / 32;
+    if (b >= nblocks) return;
+    const int bi = (int)(b / a.C), bj = (int)(b % a.C);
+    const int br = bi * bs, bc = bj * bs;
+    GenericEval<PNORM> e;
+    e.prev_block = a.prev + (size_t)plane * a.prev_stride + (size_t)br * a.pitch + bc;
+    e.cur_plane = a.cur + (size_t)plane * a.cur_stride;
+    e.pitch = a.pitch;
+    e.bs = bs;
+    e.lane = threadIdx.x & 31;
+    int o0, o1;
+    run_search(e, a.procedure, bs, a.sw, a.H, a.W, br, bc, o0, o1);
+    if (e.lane == 0) {
+        int32_t *f = a.field + ((size_t)plane * nblocks + b) * 2;
+        f[0] = o0;
+        f[1] = o1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host launcher
+// ---------------------------------------------------------------------------------------
+template <int BS, int G, int PNORM>
+static int launch_fast(PatternArgs a, int n, cudaStream_t stream)
+{
+    constexpr int NT = 256;
+    // tile: about 128 x 64 pixels of macroblocks, margin sized to typical motion; the window row
+    // length is = 16 (mod 32) bytes so that consecutive rows start 4 banks apart (conflict-free
+    // for 8 rows x 4 words, the footprint of one warp-wide unit load)
+    int tbx = max(1, 128 / BS), tby = max(1, 64 / BS);
+    if (BS <= 4) { tbx = 64 / BS; tby = 32 / BS; }
+    tbx = min(tbx, a.C);
+    tby = min(tby, a.R);
+    const int margin = (BS <= 4) ? 12 : 32;
+    int win_w = tbx * BS + 2 * margin + 4;               // +4: the funnel shift reads one word beyond the block
+    win_w = (win_w + 15) / 16 * 16;
+    if (win_w % 32 == 0) win_w += 16;
+    const int win_h = tby * BS + 2 * margin;
+    if (win_w > 256 || win_h > 256) return GME_ERR_UNSUPPORTED;   // TMA box limit; not reachable with the tiles above
+    a.tbx = tbx; a.tby = tby; a.margin = margin; a.win_w = win_w; a.win_h = win_h;
+    CUtensorMap map;
+    a.use_tma = make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h) ? 1 : 0;
+    if (!a.use_tma) memset(&map, 0, sizeof(map));
+    const size_t smem = (size_t)win_w * win_h + 32;      // slack for the trailing word of the last row
+    auto kern = bbme_pattern_kernel<BS, G, PNORM, NT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
+    kern<<<grid, NT, smem, stream>>>(map, a);
+    note_launch();
+    return check_launch("bbme_pattern_kernel");
+}
+
+template <int PNORM>
+static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
+{
+    switch (bs) {
+    case 2: return launch_fast<2, 1, PNORM>(a, n, stream);
+    case 4: return launch_fast<4, 1, PNORM>(a, n, stream);
+    case 8: return launch_fast<8, 4, PNORM>(a, n, stream);
+    case 12: return launch_fast<12, 4, PNORM>(a, n, stream);
+    case 16: return launch_fast<16, 16, PNORM>(a, n, stream);
+    default: break;
+    }
+    const long nblocks = (long)a.R * a.C;
+    const int warps = 8;
+    dim3 grid((unsigned)((nblocks + warps - 1) / warps), 1, n);
+    bbme_pattern_generic_kernel<PNORM><<<grid, warps * 32, 0, stream>>>(a, bs);
+    note_launch();
+    return check_launch("bbme_pattern_generic_kernel");
+}
+
+int launch_bbme_pattern(const uint8_t *prev, size_t prev_stride, const uint8_t *cur, size_t cur_stride, int n, int H,
+                        int W, size_t pitch, int bs, int sw, int procedure, int pnorm, int32_t *field,
+                        cudaStream_t stream)
+{
+    PatternArgs a{};
+    a.prev = prev; a.prev_stride = prev_stride;
+    a.cur = cur; a.cur_stride = cur_stride;
+    a.H = H; a.W = W; a.pitch = pitch;
+    a.R = H / bs; a.C = W / bs;
+    a.sw = sw; a.procedure = procedure;
+    a.field = field;
+    if (a.R == 0 || a.C == 0 || n == 0) return GME_OK;
+    return pnorm == GME_PNORM_MAE ? launch_pattern_pn<GME_PNORM_MAE>(a, n, bs, stream)
+                                  : launch_pattern_pn<GME_PNORM_MSE>(a, n, bs, stream);
+}
+
+}  // namespace gme

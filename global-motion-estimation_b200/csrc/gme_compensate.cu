@@ -1,0 +1,199 @@
+// gme_compensate.cu -- block-wise motion compensation fused with the PSNR error sum (K5+K6).
+//
+// Replaces motion.compensate_frame (motion.py:289-321) and the squared-error sum of
+// utils.PSNR (utils.py:100-116).  The reference's "affine warp" is a per-block integer
+// translation gather: comp[a, b] = frame[a - d1, b - d0] when the source pixel is inside the
+// frame, else frame[a, b]; rows/columns past the last whole block are copied.  HBM-bound:
+// algorithmic traffic = read frame + read cur + write comp = 3*H*W bytes per pair.
+//
+// A thread owns 16 consecutive pixels of one row: when they share one motion vector and the
+// source run is inside the frame it gathers them with (at most 5) aligned 32-bit loads and
+// funnel shifts, reads the 16 pixels of `cur` with one 128-bit load, accumulates the squared
+// error with VABSDIFF4 + IDP.4A and writes one 128-bit store.  Anything else (frame borders,
+// block sizes that are not multiples of 16, unaligned planes) takes a per-pixel path.
+#include "gme_common.cuh"
+
+namespace gme {
+
+struct CompArgs {
+    const uint8_t *frame; size_t fp, fstride;
+    const void *field; int field_is_i16; int R, C, bs;
+    const uint8_t *cur; size_t cp, cstride;
+    uint8_t *comp; size_t op, ostride;
+    int H, W;
+    int vec_ok;
+    unsigned long long *sse;
+};
+
+__device__ __forceinline__ void load_vector(const CompArgs &a, int plane, int i, int j, int &d0, int &d1)
+{
+    const size_t idx = (((size_t)plane * a.R + i) * a.C + j) * 2;
+    if (a.field_is_i16) {
+        const short2 v = *reinterpret_cast<const short2 *>(static_cast<const int16_t *>(a.field) + idx);
+        d0 = v.x; d1 = v.y;
+    } else {
+        const int2 v = *reinterpret_cast<const int2 *>(static_cast<const int32_t *>(a.field) + idx);
+        d0 = v.x; d1 = v.y;
+    }
+}
+
+__device__ __forceinline__ unsigned int block_sum_u32_to_u64(unsigned int v, unsigned long long *dst)
+{
+    __shared__ unsigned int warp_sums[32];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nwarps = (blockDim.x * blockDim.y + 31) / 32;
+    if ((tid & 31) == 0) warp_sums[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nwarps; w++) t += warp_sums[w];
+        if (t) atomicAdd(dst, t);
+    }
+    return v;
+}
+
+template <bool HAS_CUR>
+__global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
+{
+    const int plane = blockIdx.z;
+    const int a_row = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    unsigned int err = 0;
+    if (a_row < a.H && b0 < a.W) {
+        const uint8_t *fplane = a.frame + (size_t)plane * a.fstride;
+        const uint8_t *frow = fplane + (size_t)a_row * a.fp;
+        uint8_t *orow = a.comp + (size_t)plane * a.ostride + (size_t)a_row * a.op;
+        const uint8_t *crow = HAS_CUR ? a.cur + (size_t)plane * a.cstride + (size_t)a_row * a.cp : nullptr;
+        const int npx = min(16, a.W - b0);
+        const int i = a_row / a.bs, j0 = b0 / a.bs;
+        bool fast = a.vec_ok && npx == 16 && j0 == (b0 + 15) / a.bs;
+        uint32_t px[4];
+        if (fast) {
+            if (i < a.R && j0 < a.C) {
+                int d0, d1;
+                load_vector(a, plane, i, j0, d0, d1);
+                const long na = (long)a_row - d1, nb = (long)b0 - d0;       // motion.py:312-313
+                if (na >= 0 && na < a.H && nb >= 0 && nb + 15 < a.W) {
+                    const uint8_t *src = fplane + (size_t)na * a.fp + nb;
+                    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
+                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - mis);
+                    uint32_t r[5];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) r[k] = __ldg(sw + k);
+                    r[4] = mis ? __ldg(sw + 4) : 0u;                         // never touch a word with no wanted byte
+#pragma unroll
+                    for (int k = 0; k < 4; k++) px[k] = __funnelshift_r(r[k], r[k + 1], mis * 8);
+                } else if (na >= 0 && na < a.H && nb + 15 >= 0 && nb < a.W) {
+                    fast = false;                                            // run straddles the frame edge
+                } else {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(frow + b0);   // whole run out of frame: unchanged
+                    px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+                }
+            } else {
+                const uint4 v = *reinterpret_cast<const uint4 *>(frow + b0);       // past the last whole block: copied
+                px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+            }
+        }
+        if (fast) {
+            *reinterpret_cast<uint4 *>(orow + b0) = make_uint4(px[0], px[1], px[2], px[3]);
+            if (HAS_CUR) {
+                const uint4 c = *reinterpret_cast<const uint4 *>(crow + b0);
+                err = ssd4_acc(px[0], c.x, err);
+                err = ssd4_acc(px[1], c.y, err);
+                err = ssd4_acc(px[2], c.z, err);
+                err = ssd4_acc(px[3], c.w, err);
+            }
+        } else {
+            for (int k = 0; k < npx; k++) {
+                const int b = b0 + k, j = b / a.bs;
+                uint8_t v = frow[b];
+                if (i < a.R && j < a.C) {
+                    int d0, d1;
+                    load_vector(a, plane, i, j, d0, d1);
+                    const long na = (long)a_row - d1, nb = (long)b - d0;
+                    if (na >= 0 && na < a.H && nb >= 0 && nb < a.W) v = fplane[(size_t)na * a.fp + nb];
+                }
+                orow[b] = v;
+                if (HAS_CUR) {
+                    const int d = (int)v - (int)crow[b];
+                    err += (unsigned int)(d * d);
+                }
+            }
+        }
+    }
+    if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + plane);
+}
+
+__global__ void __launch_bounds__(256) sse_kernel(const uint8_t *x, size_t xp, size_t xstride, const uint8_t *y,
+                                                  size_t yp, size_t ystride, int H, int W, int vec_ok,
+                                                  unsigned long long *sse)
+{
+    const int plane = blockIdx.z;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    unsigned int err = 0;
+    if (r < H && c0 < W) {
+        const uint8_t *xr = x + (size_t)plane * xstride + (size_t)r * xp + c0;
+        const uint8_t *yr = y + (size_t)plane * ystride + (size_t)r * yp + c0;
+        if (vec_ok && c0 + 16 <= W) {
+            const uint4 u = *reinterpret_cast<const uint4 *>(xr), v = *reinterpret_cast<const uint4 *>(yr);
+            err = ssd4_acc(u.x, v.x, err);
+            err = ssd4_acc(u.y, v.y, err);
+            err = ssd4_acc(u.z, v.z, err);
+            err = ssd4_acc(u.w, v.w, err);
+        } else {
+            for (int k = 0; k < min(16, W - c0); k++) {
+                const int d = (int)xr[k] - (int)yr[k];
+                err += (unsigned int)(d * d);
+            }
+        }
+    }
+    block_sum_u32_to_u64(err, sse + plane);
+}
+
+static inline bool aligned16(const void *p, size_t pitch, size_t stride)
+{
+    return ((reinterpret_cast<uintptr_t>(p) | pitch | stride) % 16) == 0;
+}
+
+int launch_compensate(const uint8_t *frame, size_t fp, size_t fstride, const void *field, int field_is_i16, int R,
+                      int C, const uint8_t *cur, size_t cp, size_t cstride, uint8_t *comp, size_t op, size_t ostride,
+                      int n, int H, int W, uint64_t *sse, cudaStream_t stream)
+{
+    CompArgs a;
+    a.frame = frame; a.fp = fp; a.fstride = fstride;
+    a.field = field; a.field_is_i16 = field_is_i16;
+    a.bs = (R > 0) ? H / R : 0;                                   // motion.py:303: rows only
+    if (a.bs <= 0) { a.bs = 1; a.R = 0; a.C = 0; } else { a.R = R; a.C = C; }   // bs == 0: the reference's loops are empty
+    a.cur = cur; a.cp = cp; a.cstride = cstride;
+    a.comp = comp; a.op = op; a.ostride = ostride;
+    a.H = H; a.W = W;
+    a.vec_ok = (aligned16(frame, fp, fstride) && aligned16(comp, op, ostride) && (!cur || aligned16(cur, cp, cstride))) ? 1 : 0;
+    a.sse = reinterpret_cast<unsigned long long *>(sse);
+    dim3 block(32, 8);
+    dim3 grid(((W + 15) / 16 + block.x - 1) / block.x, (H + block.y - 1) / block.y, n);
+    if (cur && sse) {
+        cudaMemsetAsync(sse, 0, sizeof(uint64_t) * n, stream);
+        compensate_kernel<true><<<grid, block, 0, stream>>>(a);
+    } else {
+        compensate_kernel<false><<<grid, block, 0, stream>>>(a);
+    }
+    note_launch();
+    return check_launch("compensate_kernel");
+}
+
+int launch_sse(const uint8_t *x, size_t xp, size_t xstride, const uint8_t *y, size_t yp, size_t ystride, int n, int H,
+               int W, uint64_t *sse, cudaStream_t stream)
+{
+    const int vec_ok = (aligned16(x, xp, xstride) && aligned16(y, yp, ystride)) ? 1 : 0;
+    dim3 block(32, 8);
+    dim3 grid(((W + 15) / 16 + block.x - 1) / block.x, (H + block.y - 1) / block.y, n);
+    cudaMemsetAsync(sse, 0, sizeof(uint64_t) * n, stream);
+    sse_kernel<<<grid, block, 0, stream>>>(x, xp, xstride, y, yp, ystride, H, W, vec_ok,
+                                           reinterpret_cast<unsigned long long *>(sse));
+    note_launch();
+    return check_launch("sse_kernel");
+}
+
+}  // namespace gme

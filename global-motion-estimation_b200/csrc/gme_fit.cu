@@ -1,0 +1,311 @@
+// gme_fit.cu -- the affine global-motion fit (K4): first estimate, model field, outlier
+// mask and masked least squares.  KB-scale data, latency-bound: one CTA per frame pair.
+//
+// Replaces motion.compute_first_parameters (motion.py:176-188), parameter_projection
+// (motion.py:191-207), affine_model / get_motion_field_affine (motion.py:91-105,139-157)
+// and the fit of best_affine_parameters[_robust] (motion.py:33-88, 210-286).
+//
+// Everything that must be bit-exact is integer: the L1 differences, the order-statistic
+// threshold (exact radix select instead of the reference's sort) and the twelve masked sums
+// of the normal equations (int64, so the sums are exact; the reference accumulates the same
+// terms in float64 with one rounding per block).  Only the final 3x3 solve is floating
+// point: LU with partial pivoting + unit-lower/upper solves of the identity, the sequence
+// LAPACK's dgesv uses for np.linalg.inv, then the 3x3 matrix-vector product.  Stated
+// tolerance on the parameters: 1e-9 absolute and relative (tests/).
+#include "gme_common.cuh"
+
+namespace gme {
+
+constexpr int kFitThreads = 256;
+
+__device__ __forceinline__ long long block_sum_ll(long long v, long long *scratch /* >= 8 */)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();   // scratch reuse
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kFitThreads / 32; w++) t += scratch[w];
+    return t;
+}
+
+// motion.compute_first_parameters: mean of each channel in float64 (exact integer sum / count),
+// cast to float32 (motion.py:186-188); carried as float64 (exact promotion).
+__global__ void __launch_bounds__(kFitThreads) first_params_kernel(const int32_t *dense, long N, double *params)
+{
+    __shared__ long long scratch[8];
+    const int32_t *f = dense + (size_t)blockIdx.x * N * 2;
+    long long s0 = 0, s1 = 0;
+    for (long i = threadIdx.x; i < N; i += kFitThreads) {
+        const int2 v = *reinterpret_cast<const int2 *>(f + 2 * i);
+        s0 += v.x;
+        s1 += v.y;
+    }
+    s0 = block_sum_ll(s0, scratch);
+    s1 = block_sum_ll(s1, scratch);
+    if (threadIdx.x == 0) {
+        double *p = params + (size_t)blockIdx.x * 6;
+        p[0] = (double)(float)((double)s0 / (double)N);
+        p[1] = 0.0; p[2] = 0.0;
+        p[3] = (double)(float)((double)s1 / (double)N);
+        p[4] = 0.0; p[5] = 0.0;
+    }
+}
+
+// affine_model (motion.py:102-104): [[1,i,j,0,0,0],[0,0,0,1,i,j]] @ p in float64, then Python round() =
+// round-half-to-even.  np.matmul gives this product to BLAS dgemv, so the summation order is the
+// BLAS kernel's: d0 = (a0 + j*a2) + i*a1 without contraction, d1 = b0 + fma(i, b1, j*b2) -- pinned against
+// live NumPy (OpenBLAS 0.3.30) on 50 000 random cases, see oracle/gme_oracle.c.  Only matters within 1 ulp
+// of a .5 tie.
+__device__ __forceinline__ void model_vector(const double *p, int i, int j, int &m0, int &m1)
+{
+    const double di = (double)i, dj = (double)j;
+    const double d0 = __dadd_rn(__dadd_rn(p[0], __dmul_rn(dj, p[2])), __dmul_rn(di, p[1]));
+    const double d1 = __dadd_rn(p[3], __fma_rn(di, p[4], __dmul_rn(dj, p[5])));
+    m0 = (int)(int16_t)__double2int_rn(d0);   // stored as int16 (motion.py:150)
+    m1 = (int)(int16_t)__double2int_rn(d1);
+}
+
+__global__ void affine_field_kernel(const double *params, int R, int C, int16_t *field)
+{
+    const long N = (long)R * C;
+    const double *p = params + (size_t)blockIdx.y * 6;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N) return;
+    int m0, m1;
+    model_vector(p, (int)(idx / C), (int)(idx % C), m0, m1);
+    *reinterpret_cast<short2 *>(field + ((size_t)blockIdx.y * N + idx) * 2) = make_short2((short)m0, (short)m1);
+}
+
+struct FitArgs {
+    const int32_t *gt;
+    int R, C;
+    double w;        // 1 / (level_h * level_w)   (motion.py:250)
+    double pct;      // MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE
+    int robust, project;
+    double *params;
+    uint8_t *outlier;
+    int32_t *threshold;
+    int16_t *model_field;
+    int32_t *status;
+    int status_or;   // OR into status instead of overwriting (pipeline: a singular level must stay flagged)
+};
+
+// 3x3 inverse the way np.linalg.inv gets it (dgesv on the identity): LU with partial pivoting,
+// multipliers by reciprocal (dgetf2), forward / backward substitution per identity column.
+__device__ bool inverse3(const double (&A)[3][3], double (&inv)[3][3])
+{
+    double lu[3][3];
+    int piv[3] = {0, 1, 2};
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) lu[r][c] = A[r][c];
+    for (int k = 0; k < 3; k++) {
+        int p = k;
+        double big = fabs(lu[k][k]);
+        for (int r = k + 1; r < 3; r++)
+            if (fabs(lu[r][k]) > big) { big = fabs(lu[r][k]); p = r; }
+        if (big == 0.0 || big != big) return false;              // exactly singular -> LinAlgError in the reference
+        if (p != k) {
+            for (int c = 0; c < 3; c++) { const double t = lu[k][c]; lu[k][c] = lu[p][c]; lu[p][c] = t; }
+            const int t = piv[k]; piv[k] = piv[p]; piv[p] = t;
+        }
+        const double rcp = __ddiv_rn(1.0, lu[k][k]);
+        for (int r = k + 1; r < 3; r++) {
+            lu[r][k] = __dmul_rn(lu[r][k], rcp);
+            for (int c = k + 1; c < 3; c++) lu[r][c] = __dsub_rn(lu[r][c], __dmul_rn(lu[r][k], lu[k][c]));
+        }
+    }
+    for (int col = 0; col < 3; col++) {
+        double y[3];
+        for (int r = 0; r < 3; r++) {                            // L y = P e_col
+            double v = (piv[r] == col) ? 1.0 : 0.0;
+            for (int c = 0; c < r; c++) v = __dsub_rn(v, __dmul_rn(lu[r][c], y[c]));
+            y[r] = v;
+        }
+        for (int r = 2; r >= 0; r--) {                           // U x = y
+            double v = y[r];
+            for (int c = r + 1; c < 3; c++) v = __dsub_rn(v, __dmul_rn(lu[r][c], inv[c][col]));
+            inv[r][col] = __ddiv_rn(v, lu[r][r]);
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kFitThreads) affine_fit_kernel(FitArgs a)
+{
+    __shared__ long long scratch[8];
+    __shared__ unsigned int hist[2048];
+    __shared__ unsigned int chunk_sum[kFitThreads];
+    __shared__ double p[6];
+    __shared__ unsigned int sel_prefix, sel_rank;
+
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const long N = (long)a.R * a.C;
+    const int32_t *gt = a.gt + (size_t)pair * N * 2;
+    double *params = a.params + (size_t)pair * 6;
+
+    if (tid < 6) {
+        double v = params[tid];
+        if (a.project && (tid == 0 || tid == 3)) v = v * 2.0;    // motion.parameter_projection (motion.py:204-207)
+        p[tid] = v;
+    }
+    __syncthreads();
+
+    // ---- L1 distance between the BBME field and the model field (motion.py:232-239) --------
+    auto diff_at = [&](long idx) -> unsigned int {
+        int m0, m1;
+        model_vector(p, (int)(idx / a.C), (int)(idx % a.C), m0, m1);
+        const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * idx);
+        return (unsigned int)(abs(g.x - m0) + abs(g.y - m1));
+    };
+
+    unsigned int thr = 0xFFFFFFFFu;
+    if (a.robust) {
+        // threshold = sorted(diff)[N - int(pct*N)]  (element 0 when int(pct*N) == 0: Python's [-0])
+        const long t = (long)(a.pct * (double)N);
+        unsigned int rank = (unsigned int)(t == 0 ? 0 : N - t);   // 0-based rank of the threshold
+        unsigned int prefix = 0;                                   // bits of the answer found so far
+        unsigned int dmax = 0;
+        for (long i = tid; i < N; i += kFitThreads) {
+            const unsigned int d = diff_at(i);
+            dmax = max(dmax, d);
+            if (a.model_field) {
+                int m0, m1;
+                model_vector(p, (int)(i / a.C), (int)(i % a.C), m0, m1);
+                *reinterpret_cast<short2 *>(a.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xFFFFFFFFu, dmax, o));
+        if ((tid & 31) == 0) scratch[tid >> 5] = dmax;
+        __syncthreads();
+        dmax = 0;
+        for (int w = 0; w < kFitThreads / 32; w++) dmax = max(dmax, (unsigned int)scratch[w]);
+        __syncthreads();
+        // exact radix select, 11 bits per pass, starting at the highest digit that is populated
+        int shift = 0;
+        while (shift + 11 < 32 && (dmax >> (shift + 11)) != 0) shift += 11;
+        for (; shift >= 0; shift -= 11) {
+            for (int i = tid; i < 2048; i += kFitThreads) hist[i] = 0;
+            __syncthreads();
+            const unsigned int hi_mask = (shift + 11 >= 32) ? 0u : (0xFFFFFFFFu << (shift + 11));
+            for (long i = tid; i < N; i += kFitThreads) {
+                const unsigned int d = diff_at(i);
+                if ((d & hi_mask) == prefix) atomicAdd(&hist[(d >> shift) & 2047u], 1u);
+            }
+            __syncthreads();
+            // each thread owns 8 consecutive bins; block-wide exclusive scan of the chunk sums
+            unsigned int local[8], s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { local[k] = hist[tid * 8 + k]; s += local[k]; }
+            chunk_sum[tid] = s;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned int run = 0;
+                for (int k = 0; k < kFitThreads; k++) { const unsigned int c = chunk_sum[k]; chunk_sum[k] = run; run += c; }
+            }
+            __syncthreads();
+            const unsigned int before = chunk_sum[tid];
+            if (rank >= before && rank < before + s) {             // exactly one thread
+                unsigned int run = before;
+                for (int k = 0; k < 8; k++) {
+                    if (rank < run + local[k]) {
+                        sel_prefix = prefix | ((unsigned int)(tid * 8 + k) << shift);
+                        sel_rank = rank - run;
+                        break;
+                    }
+                    run += local[k];
+                }
+            }
+            __syncthreads();
+            prefix = sel_prefix;
+            rank = sel_rank;
+            __syncthreads();
+        }
+        thr = prefix;
+    } else if (a.model_field) {
+        for (long i = tid; i < N; i += kFitThreads) {
+            int m0, m1;
+            model_vector(p, (int)(i / a.C), (int)(i % a.C), m0, m1);
+            *reinterpret_cast<short2 *>(a.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
+        }
+    }
+
+    // ---- masked normal equations (motion.py:246-282): twelve exact integer sums -----------
+    long long S[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) S[k] = 0;
+    for (long i = tid; i < N; i += kFitThreads) {
+        const bool out = a.robust ? (diff_at(i) > thr) : false;   // strict '>' (motion.py:244)
+        if (a.outlier) a.outlier[(size_t)pair * N + i] = out ? 1 : 0;
+        if (!out) {
+            const long long x = 4 * (i / a.C), y = 4 * (i % a.C);  // motion.py:254-255
+            const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * i);
+            S[0] += 1;      S[1] += x;          S[2] += y;
+            S[3] += x * x;  S[4] += x * y;      S[5] += y * y;
+            S[6] += g.x;    S[7] += x * g.x;    S[8] += y * g.x;
+            S[9] += g.y;    S[10] += x * g.y;   S[11] += y * g.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) S[k] = block_sum_ll(S[k], scratch);
+
+    if (tid == 0) {
+        const double w = a.w;
+        double M[3][3], inv[3][3];
+        M[0][0] = (double)S[0] * w; M[0][1] = (double)S[1] * w; M[0][2] = (double)S[2] * w;
+        M[1][0] = M[0][1];          M[1][1] = (double)S[3] * w; M[1][2] = (double)S[4] * w;
+        M[2][0] = M[0][2];          M[2][1] = M[1][2];          M[2][2] = (double)S[5] * w;
+        const double r0[3] = {(double)S[6] * w, (double)S[7] * w, (double)S[8] * w};
+        const double r1[3] = {(double)S[9] * w, (double)S[10] * w, (double)S[11] * w};
+        int st = 0;
+        if (inverse3(M, inv)) {
+            for (int r = 0; r < 3; r++) {
+                params[r] = __dadd_rn(__dadd_rn(__dmul_rn(inv[r][0], r0[0]), __dmul_rn(inv[r][1], r0[1])),
+                                      __dmul_rn(inv[r][2], r0[2]));
+                params[3 + r] = __dadd_rn(__dadd_rn(__dmul_rn(inv[r][0], r1[0]), __dmul_rn(inv[r][1], r1[1])),
+                                          __dmul_rn(inv[r][2], r1[2]));
+            }
+        } else {
+            st = 1;
+            const double qnan = __longlong_as_double(0x7FF8000000000000LL);
+            for (int r = 0; r < 6; r++) params[r] = qnan;
+        }
+        if (a.status) a.status[pair] = a.status_or ? (a.status[pair] | st) : st;
+        if (a.threshold) a.threshold[pair] = a.robust ? (int32_t)thr : 0;
+    }
+}
+
+int launch_first_params(const int32_t *dense, int n, int R, int C, double *params, cudaStream_t stream)
+{
+    first_params_kernel<<<n, kFitThreads, 0, stream>>>(dense, (long)R * C, params);
+    note_launch();
+    return check_launch("first_params_kernel");
+}
+
+int launch_affine_fit(const int32_t *gt, int n, int R, int C, int level_h, int level_w, double pct, int robust,
+                      int project, double *params, uint8_t *outlier, int32_t *threshold, int16_t *model_field,
+                      int32_t *status, int status_or, cudaStream_t stream)
+{
+    FitArgs a;
+    a.gt = gt; a.R = R; a.C = C;
+    a.w = 1.0 / (double)((long long)level_h * level_w);
+    a.pct = pct; a.robust = robust; a.project = project;
+    a.params = params; a.outlier = outlier; a.threshold = threshold; a.model_field = model_field; a.status = status; a.status_or = status_or;
+    affine_fit_kernel<<<n, kFitThreads, 0, stream>>>(a);
+    note_launch();
+    return check_launch("affine_fit_kernel");
+}
+
+int launch_affine_field(const double *params, int n, int R, int C, int16_t *field, cudaStream_t stream)
+{
+    const long N = (long)R * C;
+    dim3 grid((unsigned)((N + 255) / 256), n);
+    affine_field_kernel<<<grid, 256, 0, stream>>>(params, R, C, field);
+    note_launch();
+    return check_launch("affine_field_kernel");
+}
+
+}  // namespace gme

@@ -1,0 +1,291 @@
+"""Device-side host logic of the B200 GME path: PyTorch owns the HBM buffers and the streams,
+the kernels live in libgme_b200.so (gme_native).  Everything here needs a CUDA device; there
+is no CPU fallback.
+
+Data layout in HBM
+  * frames: ``Planes`` = uint8[n, H, pitch] with pitch = W rounded up to 16 bytes, so that every
+    row is 16-byte aligned (128-bit loads, TMA boxes).  A sequence is ONE such buffer; the
+    (previous, current) pairs at frame distance d are two views of it offset by d planes, so
+    no frame is ever copied to form a pair.
+  * motion fields: int32[n, R, C, 2] (channel 0 = column displacement, 1 = row displacement).
+  * affine parameters: float64[n, 6] = [a0, a1, a2, b0, b1, b2] per pair.
+"""
+from __future__ import annotations
+
+import cmath
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+import gme_native as N
+
+PITCH_ALIGN = 16
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("the GME kernels need a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _round_up(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+@dataclass
+class Planes:
+    """n grayscale planes resident in HBM: ``t`` is uint8[n, H, pitch]; the first W columns are pixels."""
+    t: torch.Tensor
+    W: int
+
+    @property
+    def n(self) -> int:
+        return self.t.shape[0]
+
+    @property
+    def H(self) -> int:
+        return self.t.shape[1]
+
+    @property
+    def pitch(self) -> int:
+        return self.t.stride(1)
+
+    @property
+    def stride(self) -> int:
+        return self.t.stride(0)
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+    @staticmethod
+    def empty(n: int, H: int, W: int, device=None) -> "Planes":
+        device = device or require_cuda()
+        return Planes(torch.empty((n, H, _round_up(W, PITCH_ALIGN)), dtype=torch.uint8, device=device), W)
+
+    @staticmethod
+    def from_host(frames, device=None, non_blocking: bool = False) -> "Planes":
+        """frames: uint8 ndarray/tensor [H, W] or [n, H, W] (host).  One host->device copy."""
+        device = device or require_cuda()
+        if isinstance(frames, np.ndarray):
+            a = np.ascontiguousarray(frames, dtype=np.uint8)
+            src = torch.from_numpy(a)
+        else:
+            src = frames
+        if src.dim() == 2:
+            src = src.unsqueeze(0)
+        if src.dim() != 3 or src.dtype != torch.uint8:
+            raise ValueError("expected uint8 frames of shape [H, W] or [n, H, W]")
+        n, H, W = src.shape
+        p = Planes.empty(n, H, W, device)
+        p.t[:, :, :W].copy_(src, non_blocking=non_blocking)
+        return p
+
+    def view(self, start: int, stop: int) -> "Planes":
+        return Planes(self.t[start:stop], self.W)
+
+    def pixels(self) -> torch.Tensor:
+        return self.t[:, :, :self.W]
+
+    def to_host(self) -> np.ndarray:
+        return self.pixels().cpu().numpy()
+
+
+# --------------------------------------------------------------------------- single kernels
+def motion_field(prev: Planes, cur: Planes, block_size: int, search_window: int, procedure: int,
+                 pnorm: int) -> torch.Tensor:
+    """bbme.get_motion_field for n pairs -> int32[n, H//bs, W//bs, 2] on the device."""
+    if prev.t.shape != cur.t.shape or prev.W != cur.W or prev.pitch != cur.pitch:
+        raise ValueError("previous and current must have the same geometry")
+    if not 0 <= int(procedure) <= 3 or not 0 <= int(pnorm) <= 1:
+        raise IndexError("list index out of range")      # bbme.searching_procedures / pnorm_distances
+    bs = int(block_size)
+    if bs <= 0:
+        raise ZeroDivisionError("division by zero") if bs == 0 else ValueError("block_size must be positive")
+    R, C = int(prev.H / bs), int(prev.W / bs)
+    field = torch.zeros((prev.n, R, C, 2), dtype=torch.int32, device=prev.t.device)
+    if R * C:
+        N.check(N.lib.gme_bbme_motion_field(prev.ptr, prev.stride, cur.ptr, cur.stride, prev.n, prev.H, prev.W,
+                                            prev.pitch, bs, int(search_window), int(procedure), int(pnorm),
+                                            field.data_ptr(), _stream()), "gme_bbme_motion_field")
+    return field
+
+
+def pyr_down(src: Planes) -> Planes:
+    """One cv2.pyrDown level for n planes."""
+    dst = Planes.empty(src.n, (src.H + 1) // 2, (src.W + 1) // 2, src.t.device)
+    N.check(N.lib.gme_pyr_down(src.ptr, src.pitch, src.stride, dst.ptr, dst.pitch, dst.stride, src.n, src.H, src.W,
+                               _stream()), "gme_pyr_down")
+    return dst
+
+
+def first_parameters(dense_field: torch.Tensor) -> torch.Tensor:
+    n, R, C, _ = dense_field.shape
+    params = torch.empty((n, 6), dtype=torch.float64, device=dense_field.device)
+    N.check(N.lib.gme_first_parameters(dense_field.data_ptr(), n, R, C, params.data_ptr(), _stream()),
+            "gme_first_parameters")
+    return params
+
+
+def affine_fit(gt_field: torch.Tensor, level_shape, params: torch.Tensor, robust: bool = True,
+               project: bool = False, pct: float = .3, intermediates: bool = False):
+    """In-place update of params (float64[n, 6]).  Returns (params, status[, outlier, threshold, model])."""
+    n, R, C, _ = gt_field.shape
+    dev = gt_field.device
+    status = torch.zeros((n,), dtype=torch.int32, device=dev)
+    outlier = threshold = model = None
+    if intermediates:
+        outlier = torch.zeros((n, R, C), dtype=torch.uint8, device=dev)
+        threshold = torch.zeros((n,), dtype=torch.int32, device=dev)
+        model = torch.zeros((n, R, C, 2), dtype=torch.int16, device=dev)
+    N.check(N.lib.gme_affine_fit(gt_field.data_ptr(), n, R, C, int(level_shape[0]), int(level_shape[1]), float(pct),
+                                 int(robust), int(project), params.data_ptr(),
+                                 outlier.data_ptr() if intermediates else None,
+                                 threshold.data_ptr() if intermediates else None,
+                                 model.data_ptr() if intermediates else None, status.data_ptr(), _stream()),
+            "gme_affine_fit")
+    if intermediates:
+        return params, status, outlier, threshold, model
+    return params, status
+
+
+def affine_field(params: torch.Tensor, R: int, C: int) -> torch.Tensor:
+    n = params.shape[0]
+    field = torch.zeros((n, R, C, 2), dtype=torch.int16, device=params.device)
+    N.check(N.lib.gme_affine_field(params.data_ptr(), n, R, C, field.data_ptr(), _stream()), "gme_affine_field")
+    return field
+
+
+def compensate(frame: Planes, field: torch.Tensor, cur: Planes | None = None):
+    """motion.compensate_frame for n planes; with ``cur`` also the squared error sums (int64[n])."""
+    if field.dtype not in (torch.int16, torch.int32):
+        raise TypeError("motion field must be int16 or int32")
+    field = field.contiguous()
+    n, R, C = field.shape[0], field.shape[1], field.shape[2]
+    comp = Planes.empty(frame.n, frame.H, frame.W, frame.t.device)
+    sse = torch.zeros((frame.n,), dtype=torch.int64, device=frame.t.device) if cur is not None else None
+    N.check(N.lib.gme_compensate(frame.ptr, frame.pitch, frame.stride, field.data_ptr(),
+                                 int(field.dtype == torch.int16), R, C,
+                                 cur.ptr if cur is not None else None, cur.pitch if cur is not None else 0,
+                                 cur.stride if cur is not None else 0, comp.ptr, comp.pitch, comp.stride,
+                                 frame.n, frame.H, frame.W, sse.data_ptr() if sse is not None else None, _stream()),
+            "gme_compensate")
+    return comp, sse
+
+
+def sse(a: Planes, b: Planes) -> torch.Tensor:
+    out = torch.zeros((a.n,), dtype=torch.int64, device=a.t.device)
+    N.check(N.lib.gme_sse(a.ptr, a.pitch, a.stride, b.ptr, b.pitch, b.stride, a.n, a.H, a.W, out.data_ptr(),
+                          _stream()), "gme_sse")
+    return out
+
+
+def psnr_from_sse(sse_value: int, npix: int):
+    """utils.PSNR's tail (utils.py:111-116): complex result, int -1 for identical images."""
+    mse = sse_value / float(npix)
+    if mse == 0:
+        return -1
+    return 20 * cmath.log10(255.0 / cmath.sqrt(mse))
+
+
+# --------------------------------------------------------------------------- whole pipeline
+class Pipeline:
+    """motion.global_motion_estimation + model field + compensation + PSNR for batches of n pairs.
+
+    Owns the workspace and the output buffers; ``run`` enqueues the whole pipeline (12 kernel
+    launches) on the current stream without any host synchronisation, so it can be captured in
+    a CUDA graph (``capture``) and replayed."""
+
+    def __init__(self, n: int, H: int, W: int, device=None, want_comp: bool = True):
+        self.device = device or require_cuda()
+        self.n, self.H, self.W = n, H, W
+        nbytes = N.lib.gme_pipeline_workspace_bytes(n, H, W)
+        self.workspace = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=self.device)
+        self.params = torch.zeros((n, 6), dtype=torch.float64, device=self.device)
+        self.status = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        self.comp = Planes.empty(n, H, W, self.device) if want_comp else None
+        self.sse = torch.zeros((n,), dtype=torch.int64, device=self.device) if want_comp else None
+        self.graph = None
+        self._graph_key = None
+
+    def run(self, prev: Planes, cur: Planes, procedure: int = N.SEARCH_DIAMOND, window: int = 2):
+        if prev.n != self.n or prev.H != self.H or prev.W != self.W or cur.t.shape != prev.t.shape:
+            raise ValueError("pipeline geometry mismatch")
+        if prev.pitch != cur.pitch:
+            raise ValueError("previous and current must share one pitch")
+        c = self.comp
+        N.check(N.lib.gme_pipeline(prev.ptr, prev.stride, cur.ptr, cur.stride, self.n, self.H, self.W, prev.pitch,
+                                   int(procedure), int(window), self.params.data_ptr(),
+                                   c.ptr if c else None, c.pitch if c else 0, c.stride if c else 0,
+                                   self.sse.data_ptr() if c else None, self.status.data_ptr(),
+                                   self.workspace.data_ptr(), self.workspace.numel(), _stream()), "gme_pipeline")
+        return self.params, self.sse, self.status
+
+    def capture(self, prev: Planes, cur: Planes, procedure: int = N.SEARCH_DIAMOND, window: int = 2):
+        """Captures one run on (prev, cur) -- whose storage must stay alive and be refilled in place --
+        into a CUDA graph; ``replay`` then costs one graph launch."""
+        self.run(prev, cur, procedure, window)            # warm-up outside capture (module load, attributes)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(prev, cur, procedure, window)
+        self.graph = g
+        self._graph_key = (prev.ptr, cur.ptr, procedure, window)
+        return g
+
+    def replay(self):
+        self.graph.replay()
+        return self.params, self.sse, self.status
+
+    def intermediate(self, which: int) -> torch.Tensor:
+        """Views into the workspace (tests): 0 dense field, 1/2 L1/L2 fields, 3/4 L1/L2 outlier masks, 5 model field."""
+        l1 = ((self.H + 1) // 2, (self.W + 1) // 2)
+        l0 = ((l1[0] + 1) // 2, (l1[1] + 1) // 2)
+        shapes = {0: ((self.n, l0[0] // 2, l0[1] // 2, 2), torch.int32),
+                  1: ((self.n, l1[0] // 16, l1[1] // 16, 2), torch.int32),
+                  2: ((self.n, self.H // 16, self.W // 16, 2), torch.int32),
+                  3: ((self.n, l1[0] // 16, l1[1] // 16), torch.uint8),
+                  4: ((self.n, self.H // 16, self.W // 16), torch.uint8),
+                  5: ((self.n, self.H // 16, self.W // 16, 2), torch.int16)}
+        shape, dtype = shapes[which]
+        ptr = N.lib.gme_pipeline_workspace_ptr(self.workspace.data_ptr(), self.n, self.H, self.W, which)
+        off = ptr - self.workspace.data_ptr()
+        count = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off:off + count].view(dtype).view(shape)
+
+    def psnr(self):
+        """Host-side tail of utils.PSNR for every pair (one device->host read of n int64)."""
+        return [psnr_from_sse(int(s), self.H * self.W) for s in self.sse.cpu().tolist()]
+
+
+def gme_pairs(prev, cur, procedure: int = N.SEARCH_DIAMOND, window: int = 2, want_comp: bool = True):
+    """Public batched entry point with HOST buffers: uint8 [n, H, W] previous and current frames in,
+    (params float64[n, 6], psnr list, compensated uint8[n, H, W] | None) out.  Raises
+    numpy.linalg.LinAlgError like the reference if any pair hits a singular normal matrix."""
+    p, c = Planes.from_host(prev), Planes.from_host(cur)
+    pipe = Pipeline(p.n, p.H, p.W, p.t.device, want_comp)
+    pipe.run(p, c, procedure, window)
+    if int(pipe.status.max().item()) != 0:
+        raise N.singular_matrix_error()
+    params = pipe.params.cpu().numpy()
+    if not want_comp:
+        return params, None, None
+    return params, pipe.psnr(), pipe.comp.to_host()
+
+
+def gme_sequence(frames: Planes, distance: int, procedure: int = N.SEARCH_DIAMOND, window: int = 2,
+                 pipeline: Pipeline | None = None):
+    """All pairs (k, k + distance) of a device-resident sequence, the loop of results.py:41-59,109.
+    The two operands are views of the same buffer; nothing is copied."""
+    n = frames.n - distance
+    if n <= 0:
+        raise ValueError("sequence shorter than the frame distance")
+    pipe = pipeline or Pipeline(n, frames.H, frames.W, frames.t.device)
+    pipe.run(frames.view(0, n), frames.view(distance, distance + n), procedure, window)
+    return pipe

@@ -1,0 +1,140 @@
+/*
+ * gme_b200.h -- C ABI of the B200-native global-motion-estimation hot path.
+ *
+ * The reference (Samaretas/global-motion-estimation) is pure Python and has no FFI of its
+ * own: its boundary is the module surface of bbme.py / motion.py / utils.py.  These entry
+ * points are what a binding for that surface calls (ctypes stub: INTEGRATION.md); each one
+ * names the reference function it replaces (paths relative to
+ * /root/reference/global_motion_estimation/).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (no ownership transfer, no
+ *    allocation inside the library).  `stream` is a cudaStream_t passed as void*; all work
+ *    is asynchronous on it.  Thread-safe for distinct streams/buffers.
+ *  - A "plane set" is n grayscale uint8 planes of H rows x W columns: plane k starts at
+ *    base + k*plane_stride, row r at + r*pitch (bytes).  pitch % 4 == 0 is required;
+ *    pitch % 16 == 0 with 16-byte aligned bases lets the search windows travel by TMA
+ *    (otherwise a cooperative-load path is used; results are identical).
+ *    prev and cur may alias one sequence buffer (cur = prev + d*plane_stride).
+ *  - Motion fields are int32[n][R][C][2] with R = H/bs, C = W/bs; channel 0 = column
+ *    (horizontal) displacement, channel 1 = row (vertical) displacement (bbme.py:176-177).
+ *  - Return value: GME_OK, or a negative GME_ERR_* (never throws, never exits).
+ *    Kernel launch errors are returned as GME_ERR_CUDA; gme_last_cuda_error() has the code.
+ */
+#ifndef GME_B200_H
+#define GME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GME_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GME_API __attribute__((visibility("default")))
+#else
+#define GME_API
+#endif
+
+enum {
+    GME_OK = 0,
+    GME_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, bad enum            */
+    GME_ERR_UNSUPPORTED = -2,      /* geometry the reference leaves undefined (see each fn) */
+    GME_ERR_ALIGNMENT = -3,        /* pitch % 4 != 0                                        */
+    GME_ERR_CUDA = -4,             /* a CUDA runtime/driver call failed                     */
+    GME_ERR_WORKSPACE = -5         /* workspace too small                                   */
+};
+
+/* bbme.searching_procedures (bbme.py:609-614) and bbme.pnorm_distances (bbme.py:608) */
+enum { GME_SEARCH_EXHAUSTIVE = 0, GME_SEARCH_THREESTEP = 1, GME_SEARCH_TWODLOG = 2, GME_SEARCH_DIAMOND = 3 };
+enum { GME_PNORM_MAE = 0, GME_PNORM_MSE = 1 };
+
+GME_API int gme_version(void);
+GME_API const char *gme_error_string(int code);
+GME_API int gme_last_cuda_error(void);
+
+/* bbme.get_motion_field (bbme.py:12-38) + the four *_search procedures (bbme.py:105-534),
+ * batched over n frame pairs.  Anchor blocks come from prev, candidates from cur.
+ * Costs are exact integers (SAD / SSD); bit-identical to the reference's float32 sums for
+ * MAE with block_size <= 255 and MSE with block_size <= 16.
+ * GME_ERR_UNSUPPORTED: block_size > 255; diamond with H <= bs or W <= bs (bbme.py:503-504
+ * clamps to a negative bound there). */
+GME_API int gme_bbme_motion_field(const uint8_t *prev, size_t prev_plane_stride,
+                          const uint8_t *cur, size_t cur_plane_stride,
+                          int n, int H, int W, size_t pitch,
+                          int block_size, int search_window, int procedure, int pnorm,
+                          int32_t *field, void *stream);
+
+/* cv2.pyrDown as used by utils.get_pyramids (utils.py:34-51): one level, n planes.
+ * dst planes are ((H+1)/2) x ((W+1)/2). */
+GME_API int gme_pyr_down(const uint8_t *src, size_t src_pitch, size_t src_plane_stride,
+                 uint8_t *dst, size_t dst_pitch, size_t dst_plane_stride,
+                 int n, int H, int W, void *stream);
+
+/* motion.compute_first_parameters (motion.py:176-188): params[k] = [mean ch0, 0, 0, mean ch1, 0, 0]
+ * rounded through float32, stored as float64[n][6]. */
+GME_API int gme_first_parameters(const int32_t *dense_field, int n, int R, int C, double *params, void *stream);
+
+/* motion.best_affine_parameters_robust (motion.py:210-286) minus its BBME call, plus
+ * motion.parameter_projection (motion.py:191-207) when project != 0:
+ *   params (float64[n][6], in/out): old parameters in, new parameters out;
+ *   robust = 0 gives motion.best_affine_parameters (motion.py:33-88, no outlier mask);
+ *   level_h/level_w: shape of the frame the field was estimated on (w = 1/(h*w));
+ *   outlier (uint8[n][R][C]), threshold (int32[n]), model_field (int16[n][R][C][2]) are
+ *   optional outputs (may be NULL); status (int32[n], may be NULL): 0 ok, 1 = singular
+ *   normal matrix (the reference raises numpy.linalg.LinAlgError there). */
+GME_API int gme_affine_fit(const int32_t *gt_field, int n, int R, int C, int level_h, int level_w,
+                   double pct, int robust, int project, double *params,
+                   uint8_t *outlier, int32_t *threshold, int16_t *model_field, int32_t *status,
+                   void *stream);
+
+/* motion.get_motion_field_affine (motion.py:139-157): int16[n][R][C][2]. */
+GME_API int gme_affine_field(const double *params, int n, int R, int C, int16_t *field, void *stream);
+
+/* motion.compensate_frame (motion.py:289-321), fused with the squared-error sum of
+ * utils.PSNR (utils.py:100-116) against `cur` when cur != NULL:
+ *   field is int16 or int32 [n][R][C][2] (field_is_i16 selects);
+ *   comp receives the compensated planes; sse (uint64[n]) the sum of (cur-comp)^2. */
+GME_API int gme_compensate(const uint8_t *frame, size_t frame_pitch, size_t frame_plane_stride,
+                   const void *field, int field_is_i16, int R, int C,
+                   const uint8_t *cur, size_t cur_pitch, size_t cur_plane_stride,
+                   uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride,
+                   int n, int H, int W, uint64_t *sse, void *stream);
+
+/* utils.PSNR (utils.py:100-116): sse[k] = sum (a-b)^2 over plane k; the caller finishes
+ * mse = sse/(H*W), 20*log10(255/sqrt(mse)). */
+GME_API int gme_sse(const uint8_t *a, size_t a_pitch, size_t a_plane_stride,
+            const uint8_t *b, size_t b_pitch, size_t b_plane_stride,
+            int n, int H, int W, uint64_t *sse, void *stream);
+
+/* motion.global_motion_estimation + get_motion_field_affine + compensate_frame + PSNR
+ * (motion.py:109-136, results.py:50-59,109) for n frame pairs in one call.
+ * procedure/search_window apply to the block_size-16 levels only; the dense first
+ * estimate is always diamond with block_size 2 and the cost is always MSE, as in the
+ * reference (motion.py:27-29, 224-229).  Reference behaviour = (GME_SEARCH_DIAMOND, 2).
+ * Outputs: params float64[n][6]; comp (optional) + sse uint64[n] (optional, needs comp);
+ * status int32[n].  Workspace layout is private; size it with gme_pipeline_workspace_bytes. */
+GME_API size_t gme_pipeline_workspace_bytes(int n, int H, int W);
+GME_API int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride,
+                 const uint8_t *cur, size_t cur_plane_stride,
+                 int n, int H, int W, size_t pitch,
+                 int procedure, int search_window,
+                 double *params, uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride,
+                 uint64_t *sse, int32_t *status,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* Introspection for tests and the bench: pointers into a gme_pipeline workspace.
+ * which: 0 dense L0 field, 1 L1 field, 2 L2 field (int32), 3 L1 outlier mask, 4 L2 outlier
+ * mask (uint8), 5 model field at full resolution (int16). */
+GME_API void *gme_pipeline_workspace_ptr(void *workspace, int n, int H, int W, int which);
+
+/* Number of kernel launches issued through this library since load (for bench accounting). */
+GME_API uint64_t gme_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GME_B200_H */
