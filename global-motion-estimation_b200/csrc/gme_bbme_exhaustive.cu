@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(NT) bbme_exhaustive_kernel(const __grid_consta
     const int plane = blockIdx.z, bi = blockIdx.y, bj0 = blockIdx.x * a.nb;
     const int br = bi * BS, bc0 = bj0 * BS;
     const int ncand = 2 * a.sw + BS;                 // offsets per axis: [-sw, sw+bs-1]  (bbme.py:146-149)
-    const int wr0 = br - a.sw, wc0 = bc0 - a.sw;     // image coordinates of window (0, 0)
+    // image coordinates of window (0, 0); the first column is rounded down to a 16-byte boundary because
+    // TMA traps (cudaErrorIllegalInstruction) on a box whose innermost coordinate is not 16-byte aligned
+    const int wr0 = br - a.sw, wc0 = (bc0 - a.sw) & ~15;
+    const int xoff = (bc0 - a.sw) - wc0;
     const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
     const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
 
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(NT) bbme_exhaustive_kernel(const __grid_consta
         for (int ci = t_in; ci < ncand; ci += a.tpb) {
             const int left = bc + ci - a.sw;
             if (left < 0 || left > a.W - BS) continue;          // bbme.py:157-162, column part
-            const int x0 = b * BS + ci;                          // byte column inside the window
+            const int x0 = xoff + b * BS + ci;                   // byte column inside the window
             const int sh = (x0 & 3) * 8;
             const uint32_t *wp = win + (x0 >> 2);
             uint32_t acc[BS];
@@ -220,7 +223,7 @@ static int launch_fast(ExhaustiveArgs a, int n, cudaStream_t stream, bool *handl
     int tpb = min(ncand, NT);
     int nb = max(1, min(NT / tpb, a.C));
     const int win_h = 2 * a.sw + 2 * BS - 1;
-    int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4;       // +4: trailing word of the funnel shift
+    int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4 + 15;  // +4: trailing word of the funnel shift; +15: alignment
     win_w = (win_w + 15) / 16 * 16;
     const size_t win_bytes = ((size_t)win_w * win_h + 32 + 127) / 128 * 128;
     const size_t smem = win_bytes + (size_t)(nb * BS * WPR + 1) * 4 + (size_t)nb * 8 + 16;

@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(NT) bbme_pattern_kernel(const __grid_constant_
 
     const int plane = blockIdx.z;
     const int tile_r = blockIdx.y * a.tby, tile_c = blockIdx.x * a.tbx;   // first macroblock of the tile
-    const int wr0 = tile_r * BS - a.margin, wc0 = tile_c * BS - a.margin;
+    // TMA needs the box to start on a 16-byte boundary of the row (a misaligned innermost coordinate
+    // traps with cudaErrorIllegalInstruction on sm_100a): round the window's first column down to 16
+    const int wr0 = tile_r * BS - a.margin, wc0 = (tile_c * BS - a.margin) & ~15;
     const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
     const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
 
@@ -457,8 +459,8 @@ static int launch_fast(PatternArgs a, int n, cudaStream_t stream)
     tbx = min(tbx, a.C);
     tby = min(tby, a.R);
     const int margin = (BS <= 4) ? 12 : 32;
-    int win_w = tbx * BS + 2 * margin + 4;               // +4: the funnel shift reads one word beyond the block
-    win_w = (win_w + 15) / 16 * 16;
+    int win_w = tbx * BS + 2 * margin + 4 + 15;          // +4: the funnel shift reads one word beyond the block;
+    win_w = (win_w + 15) / 16 * 16;                      // +15: the first column is rounded down to 16 bytes (TMA)
     if (win_w % 32 == 0) win_w += 16;
     const int win_h = tby * BS + 2 * margin;
     if (win_w > 256 || win_h > 256) return GME_ERR_UNSUPPORTED;   // TMA box limit; not reachable with the tiles above

@@ -1,0 +1,98 @@
+"""GPU: the drop-in modules (bbme / motion / utils with the reference's names and signatures) against
+the reference's golden outputs -- these read like calls into the reference itself."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PARAM_TOL = dict(atol=1e-9, rtol=1e-9)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import gme_device
+    gme_device.require_cuda()
+    import bbme
+    import motion
+    import utils
+    return utils, bbme, motion
+
+
+def test_bbme_api(mods, golden):
+    utils, bbme, motion = mods
+    g = golden("bbme_kat")
+    prev, cur = g["prev"], g["cur"]
+    for pn in (0, 1):
+        for sp in (0, 1, 2, 3):
+            mf = bbme.get_motion_field(prev, cur, block_size=12, search_window=12, searching_procedure=sp,
+                                       pnorm_distance=pn)
+            assert mf.dtype == np.int32 and mf.shape == (20, 26, 2)
+            np.testing.assert_array_equal(mf, g[f"mf_pn{pn}_sp{sp}"])
+    # the four search functions fill and return the array they are given
+    mf = np.zeros((20, 26, 2), np.int32)
+    out = bbme.diamond_search(prev, cur, mf, 240, 320, 1, 12)
+    assert out is mf
+    np.testing.assert_array_equal(mf, g["mf_pn1_sp3"])
+    with pytest.raises(IndexError):
+        bbme.get_motion_field(prev, cur, searching_procedure=7)
+    assert bbme.compute_dfd(prev[:4, :4], cur[:4, :4], 1).dtype == np.float32
+    assert bbme.searching_procedures[3] is bbme.diamond_search and bbme.pnorm_distances[0] is bbme.mae
+
+
+def test_hierarchical_wrapper(mods, golden):
+    utils, bbme, motion = mods
+    g = golden("misc")
+    for k in range(int(g["hw_n"])):
+        bs, sw, sp = (int(v) for v in g[f"hw_a{k}"])
+        want = g[f"hw_out{k}"]
+        if want.dtype.kind == "U":
+            with pytest.raises(ValueError):
+                bbme.hierarchical_wrapper(g["hw_prev"], g["hw_cur"], bs, sw, sp)
+        else:
+            got = bbme.hierarchical_wrapper(g["hw_prev"], g["hw_cur"], block_size=bs, search_window=sw,
+                                            searching_procedure=sp)
+            assert got.dtype == np.float64
+            np.testing.assert_array_equal(got, want)
+
+
+def test_utils_api(mods, golden):
+    utils, bbme, motion = mods
+    g = golden("pyramid")
+    for k in range(int(g["n"])):
+        pyr = utils.get_pyramids(g[f"img{k}"])
+        assert len(pyr) == 3 and pyr[2] is g[f"img{k}"] or np.array_equal(pyr[2], g[f"img{k}"])
+        np.testing.assert_array_equal(pyr[1], g[f"l1_{k}"])
+        np.testing.assert_array_equal(pyr[0], g[f"l0_{k}"])
+    m = golden("misc")
+    ps = utils.PSNR(m["cf_frame"], m["cf_other"])
+    assert isinstance(ps, complex) and (ps.real, ps.imag) == tuple(m["psnr_fo"])
+    assert utils.PSNR(m["cf_frame"], m["cf_frame"]) == -1
+    draw = utils.draw_motion_field(m["cf_frame"], np.zeros((6, 8, 2), np.int32))
+    assert draw.shape == (100, 132, 3)
+
+
+@pytest.mark.parametrize("name", ["kat", "pan", "zoomrot", "odd"])
+def test_motion_api(mods, golden, name):
+    utils, bbme, motion = mods
+    g = golden("gme_pipeline")
+    prev, cur = g[f"{name}_prev"], g[f"{name}_cur"]
+    assert motion.BBME_BLOCK_SIZE == 16 and motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE == .3
+    np.testing.assert_array_equal(motion.dense_motion_estimation(prev, cur)[::7, ::5], g[f"{name}_dense"][::7, ::5])
+    first = motion.compute_first_parameters(g[f"{name}_dense"])
+    assert first.dtype == np.float32
+    np.testing.assert_array_equal(first, g[f"{name}_first"])
+    params = motion.global_motion_estimation(prev, cur)
+    assert params.dtype == np.float64 and params.shape == (6,)
+    np.testing.assert_allclose(params, g[f"{name}_params"], **PARAM_TOL)
+    shape = (prev.shape[0] // 16, prev.shape[1] // 16, 2)
+    model = motion.get_motion_field_affine(shape, g[f"{name}_params"])
+    assert model.dtype == np.int16
+    np.testing.assert_array_equal(model, g[f"{name}_modelfield"])
+    comp = motion.compensate_frame(prev, model)
+    np.testing.assert_array_equal(comp, g[f"{name}_comp"])
+    np.testing.assert_array_equal(motion.motion_compensation(prev, cur), g[f"{name}_mc"])
+    np.testing.assert_allclose(motion.best_affine_parameters(prev, cur), g[f"{name}_nonrobust"], **PARAM_TOL)
+    p = np.array([1.5, 0, 0, -2.25, 0, 0], dtype=np.float32)
+    assert motion.parameter_projection(p) is p and p[0] == 3.0 and p[3] == -4.5
+    np.testing.assert_array_equal(motion.affine_model(2, 3, params),
+                                  [params[0] + 2 * params[1] + 3 * params[2], params[3] + 2 * params[4] + 3 * params[5]])
