@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- GME frame-pairs/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the whole hot path (pyramids, dense + block BBME, robust affine fit, model field,
+compensation, PSNR sums: gme_pipeline of include/gme_b200.h) over one batch of frame pairs
+(k, k + 3) of a synthetic sequence.  `value` has the sequence resident in HBM; `e2e` is the same step
+driven with HOST (pinned) frames: host->device copy of the sequence and device->host read of the
+per-pair affine parameters + squared-error sums inside the timed region.  Frame pairs shard across
+ranks with no data-path collective; the only exchange is the all-gather of [pairs, 7] float64 rows
+(6 parameters + PSNR) at the end of each step.
+
+`--impl reference` (and the cpu_baseline object of the default arm) times the CPU port of the
+reference's pipeline (oracle/gme_oracle.c, kind "port": the reference itself is pure Python and cannot
+travel to the GPU box) on the host cores, one pair per thread.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "global-motion-estimation_b200")
+sys.path[:0] = [PKG]
+
+import numpy as np  # noqa: E402
+
+DISTANCE = 3                                   # results.py -f 3 (README default)
+
+WORKLOADS = {
+    # name: (H, W, motion, procedure, window, pairs per step per GPU, description)
+    "gme_1080p": (1080, 1920, "zoomrot", 3, 2, 64,
+                  "full GME pipeline, synthetic 1920x1080 zoom+rotate sequence, frame distance 3, reference-default "
+                  "search (diamond, MSE, bs 2/16/16)"),
+    "gme_1080p_3step": (1080, 1920, "zoomrot", 1, 16, 64,
+                        "config 4: full GME pipeline 1920x1080 zoom+rotate, three-step sw=16 on the bs-16 levels"),
+    "gme_1080p_2dlog": (1080, 1920, "zoomrot", 2, 16, 64,
+                        "config 4: full GME pipeline 1920x1080 zoom+rotate, 2D-log sw=16 on the bs-16 levels"),
+    "gme_480p": (480, 720, "pan", 3, 2, 256,
+                 "config 3: full GME pipeline, synthetic 720x480 panning sequence, frame distance 3 (diamond)"),
+    "gme_4k_exh32": (2160, 3840, "affine", 0, 32, 8,
+                     "config 5: full GME pipeline 3840x2160 affine sequence, exhaustive sw=32 on the bs-16 levels"),
+}
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic sequences (generated on the device with torch: float64 bilinear warp of a NumPy texture)
+# ----------------------------------------------------------------------------------------------
+def make_sequence(n_frames, H, W, motion, seed, device):
+    import torch
+    import gme_synth as S
+    if motion == "pan":
+        return torch.from_numpy(S.pan_sequence(n_frames, H, W, step=(2, 1), seed=seed)).to(device)
+    base = torch.from_numpy(S.texture(H, W, seed)).to(device=device, dtype=torch.float64)
+    ys, xs = torch.meshgrid(torch.arange(H, device=device, dtype=torch.float64),
+                            torch.arange(W, device=device, dtype=torch.float64), indexing="ij")
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    rng = np.random.default_rng(seed)
+    tx, ty, sc, rot, sh = rng.uniform(-1, 1, 5)
+    unit = 12.0 / 3.0 / np.hypot(cx, cy)
+    out = torch.empty((n_frames, H, W), dtype=torch.uint8, device=device)
+
+    def refl(i, n):
+        i = i.abs().to(torch.int64) % (2 * n - 2)
+        return torch.where(i >= n, 2 * n - 2 - i, i)
+
+    for k in range(n_frames):
+        if motion == "zoomrot":                      # config 4: scale 1 + 0.002 k, angle 0.1 deg * k about the centre
+            s, t, h, dx, dy = 1.0 / (1.0 + 0.002 * k), np.deg2rad(0.1 * k), 0.0, 0.0, 0.0
+        else:                                        # config 5: general affine, corner displacement <= 12 px / 3 frames
+            s, t, h = 1.0 + sc * unit * k, rot * unit * k, sh * unit * k
+            dx, dy = tx * 4.0 * k / 3.0, ty * 4.0 * k / 3.0
+        A = s * np.array([[np.cos(t), np.sin(t) + h], [-np.sin(t), np.cos(t)]])
+        b = np.array([cx, cy]) - A @ np.array([cx, cy]) + np.array([dx, dy])
+        sx = A[0, 0] * xs + A[0, 1] * ys + b[0]
+        sy = A[1, 0] * xs + A[1, 1] * ys + b[1]
+        x0, y0 = sx.floor(), sy.floor()
+        fx, fy = sx - x0, sy - y0
+        x0i, x1i, y0i, y1i = refl(x0, W), refl(x0 + 1, W), refl(y0, H), refl(y0 + 1, H)
+        top = base[y0i, x0i] * (1 - fx) + base[y0i, x1i] * fx
+        bot = base[y1i, x0i] * (1 - fx) + base[y1i, x1i] * fx
+        out[k] = (top * (1 - fy) + bot * fy).round().clamp(0, 255).to(torch.uint8)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks (sampled during the timed regions)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the CPU port of the reference pipeline (oracle; the only place bench.py runs anything under oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_pairs_per_s(frames: np.ndarray, procedure: int, window: int, n_pairs: int, cores: int):
+    """Runs n_pairs frame pairs (drawn cyclically from `frames`) through the C port of the reference's
+    pipeline -- global_motion_estimation + get_motion_field_affine + compensate_frame + PSNR
+    (results.py:50-59,109) -- one pair per thread on `cores` threads.  Returns (pairs/s, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from concurrent.futures import ThreadPoolExecutor
+    import gme_oracle as O
+    O.lib()
+    H, W = frames.shape[1:]
+    n_avail = frames.shape[0] - DISTANCE
+
+    def one(k):
+        prev, cur = frames[k % n_avail], frames[k % n_avail + DISTANCE]
+        p = O.global_motion_estimation(prev, cur, procedure=procedure, window=window)
+        comp = O.compensate_frame(prev, O.get_motion_field_affine((H // 16, W // 16), p))
+        return p, O.PSNR(cur, comp)
+
+    one(0)                                              # warm-up (library load, page-in)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(one, range(n_pairs)))
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_pair(H, W):
+    """bytes each stage must move per frame pair (uint8 pixels, int32 fields)."""
+    H1, W1 = (H + 1) // 2, (W + 1) // 2
+    H0, W0 = (H1 + 1) // 2, (W1 + 1) // 2
+    nb0, nb1, nb2 = (H0 // 2) * (W0 // 2), (H1 // 16) * (W1 // 16), (H // 16) * (W // 16)
+    return {
+        "pyramids": 2 * (H * W + 2 * H1 * W1 + H0 * W0),            # both frames: read L2, write+read L1, write L0
+        "bbme_dense_l0": 2 * H0 * W0 + 8 * nb0,
+        "bbme_l1": 2 * H1 * W1 + 8 * nb1,
+        "bbme_l2": 2 * H * W + 8 * nb2,
+        "fit": 8 * (nb0 + nb1 + nb2) + nb1 + nb2 + 48,
+        "compensate_psnr": 3 * H * W + 4 * nb2,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="gme_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    H, W, motion, procedure, window, pairs, desc = WORKLOADS[args.workload]
+    pairs = args.pairs or pairs
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric, unit = "gme_frame_pairs_per_sec", "frame-pairs/s"
+    config = {"workload": args.workload, "description": desc, "height": H, "width": W, "frame_distance": DISTANCE,
+              "pairs_per_step_per_gpu": pairs, "search_procedure": procedure, "search_window": window,
+              "l2_policy": "inputs larger than L2 (sequence + outputs per step exceed 126 MB)" if
+              (pairs + DISTANCE) * H * W * 2 > 126e6 else "L2 flushed between steps (256 MB memset)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = host_cores()
+        import gme_synth as S
+        nf = 8 + DISTANCE
+        frames = (S.pan_sequence(nf, H, W, step=(2, 1), seed=3) if motion == "pan"
+                  else S.zoom_rotate_sequence(nf, H, W, seed=4) if motion == "zoomrot"
+                  else S.affine_sequence(nf, H, W, seed=5))
+        per_step = max(2 * cores, 8)
+        for _ in range(args.warmup):
+            cpu_pairs_per_s(frames, procedure, window, cores, cores)
+        t = 0.0
+        for _ in range(args.steps):
+            _, dt = cpu_pairs_per_s(frames, procedure, window, per_step, cores)
+            t += dt
+        value = per_step * args.steps / t
+        sample = f"{per_step} pairs per step drawn cyclically from an {nf}-frame sequence, one pair per thread"
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64",
+            "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ the B200 arm
+    import torch
+    import torch.distributed as dist
+    import gme_device as D
+    import gme_distributed as GD
+    import gme_native as N
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nf = pairs + DISTANCE
+    seq = make_sequence(nf, H, W, motion, seed=4 + rank, device=dev)            # uint8[nf, H, W] on the device
+    planes = D.Planes.empty(nf, H, W, dev)
+    planes.pixels().copy_(seq)
+    host_frames = torch.empty((nf, H, W), dtype=torch.uint8, pin_memory=True)
+    host_frames.copy_(seq)
+    del seq
+    prev, cur = planes.view(0, pairs), planes.view(DISTANCE, nf)
+    pipe = D.Pipeline(pairs, H, W, dev)
+    host_out = torch.empty((pairs, 8), dtype=torch.float64, pin_memory=True)    # 6 params + sse + status
+    dev_out = torch.empty((pairs, 8), dtype=torch.float64, device=dev)
+    flush = None if "inputs larger" in config["l2_policy"] else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total_pairs = pairs * world
+
+    def rows():
+        dev_out[:, :6] = pipe.params
+        dev_out[:, 6] = pipe.sse.to(torch.float64)
+        dev_out[:, 7] = pipe.status.to(torch.float64)
+        return dev_out
+
+    def step(e2e: bool):
+        if flush is not None:
+            flush.zero_()
+        if e2e:
+            planes.pixels().copy_(host_frames, non_blocking=True)
+        pipe.run(prev, cur, procedure, window)
+        out = rows()
+        if world > 1:
+            out = GD.gather_rows(out[:, :7], total_pairs)[rank * pairs:(rank + 1) * pairs]
+            if e2e:
+                host_out[:, :7].copy_(out, non_blocking=True)
+        elif e2e:
+            host_out.copy_(out, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e: bool, steps: int, sampler, after_warmup=None):
+        for _ in range(args.warmup):
+            step(e2e)
+        barrier()
+        if after_warmup:
+            after_warmup()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with sampler:
+            start.record()
+            for _ in range(steps):
+                step(e2e)
+            end.record()
+            barrier()
+        ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    # device-resident arm, with live per-stage timing (events recorded by gme_pipeline on its stream)
+    mark = {}
+
+    def start_accounting():
+        N.stage_timing_enable(True)
+        mark["launches"] = N.launch_count()
+
+    ms_total = timed(False, args.steps, sampler, start_accounting)
+    launches = N.launch_count() - mark["launches"]
+    stage_ms, calls = N.stage_timing_read()
+    N.stage_timing_enable(False)
+    assert calls == args.steps, (calls, args.steps)
+    launches_per_step = launches // args.steps
+    value = total_pairs * args.steps / (ms_total * 1e-3)
+
+    # end-to-end arm: host frames in, per-pair results back on the host
+    ms_e2e = timed(True, args.steps, sampler)
+    e2e_value = total_pairs * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # parity spot check of what was just timed (outside the timed regions; the oracle is the checker)
+    parity = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import gme_oracle as O
+        fr = host_frames.numpy()
+        got = host_out.numpy().copy()
+        ok = True
+        for k in (0, pairs - 1):
+            want = O.global_motion_estimation(fr[k], fr[k + DISTANCE], procedure=procedure, window=window)
+            comp = O.compensate_frame(fr[k], O.get_motion_field_affine((H // 16, W // 16), want))
+            ok &= bool(np.allclose(got[k, :6], want, atol=1e-9, rtol=1e-9)) and int(got[k, 6]) == O.sse(fr[k + DISTANCE], comp)
+        parity = "ok" if ok else "MISMATCH"
+    except Exception as exc:                                                      # noqa: BLE001
+        parity = f"not checked: {exc}"
+
+    # roofline of the dominant stage, measured inside the timed region
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    bytes_pp = algorithmic_bytes_per_pair(H, W)
+    stages = {}
+    for name, ms in zip(N.STAGE_NAMES, stage_ms):
+        per_call = ms / args.steps
+        gbs = bytes_pp[name] * pairs / (per_call * 1e-3) / 1e9 if per_call > 0 else 0.0
+        stages[name] = {"ms_per_step": per_call, "share": ms / max(sum(stage_ms), 1e-12), "algorithmic_gbs": gbs,
+                        "frac_of_hbm_peak": gbs / hbm_peak}
+    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["algorithmic_gbs"], "peak": hbm_peak,
+                "unit": "GB/s", "frac": stages[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_pp[dom] * pairs,
+                "whole_step_algorithmic_gbs": sum(bytes_pp.values()) * pairs / (ms_total / args.steps * 1e-3) / 1e9}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        fr = host_frames.numpy()
+        n_cpu = max(2 * cores, 16)
+        v, dt = cpu_pairs_per_s(fr, procedure, window, n_cpu, cores)
+        while dt < 8.0 and n_cpu < 64 * cores:                                   # bounded sample of ~10-30 s
+            n_cpu *= 4
+            v, dt = cpu_pairs_per_s(fr, procedure, window, n_cpu, cores)
+        cpu = {"value": v, "unit": unit, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} pairs of the same sequence (cyclic), one pair per thread, {dt:.1f} s of wall time"}
+
+    out = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32 (fit: int64 sums + f64 solve)", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": nf * H * W,
+                "d2h_bytes_per_step": pairs * (7 if world > 1 else 8) * 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+        "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "parity": parity,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

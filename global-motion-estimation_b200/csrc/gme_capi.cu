@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "gme_common.cuh"
 
@@ -26,6 +28,39 @@ int launch_sse(const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t,
 
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_last_cuda_error{0};
+
+// ---- per-stage timing (bench only) ----------------------------------------------------
+static std::mutex g_timing_mu;
+static bool g_timing_on = false;
+static std::vector<cudaEvent_t> g_timing_events;   // (GME_PIPELINE_STAGES + 1) events per recorded call
+
+struct StageTimer {
+    cudaStream_t st;
+    bool on;
+    std::vector<cudaEvent_t> ev;
+    explicit StageTimer(cudaStream_t s) : st(s)
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        on = g_timing_on;
+    }
+    void mark()
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    }
+    ~StageTimer()
+    {
+        if (ev.empty()) return;
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        if (ev.size() == GME_PIPELINE_STAGES + 1 && g_timing_on)
+            g_timing_events.insert(g_timing_events.end(), ev.begin(), ev.end());
+        else
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+};
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -157,6 +192,38 @@ int gme_last_cuda_error(void) { return g_last_cuda_error.load(); }
 
 uint64_t gme_launch_count(void) { return g_launches.load(); }
 
+int gme_stage_timing_enable(int enable)
+{
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing_on = enable != 0;
+    for (cudaEvent_t e : g_timing_events) cudaEventDestroy(e);
+    g_timing_events.clear();
+    return GME_OK;
+}
+
+int gme_stage_timing_read(double *ms_sum, int *calls)
+{
+    if (!ms_sum || !calls) return GME_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (int s = 0; s < GME_PIPELINE_STAGES; s++) ms_sum[s] = 0.0;
+    const size_t per = GME_PIPELINE_STAGES + 1;
+    *calls = (int)(g_timing_events.size() / per);
+    int rc = GME_OK;
+    if (!g_timing_events.empty() && cudaEventSynchronize(g_timing_events.back()) != cudaSuccess) rc = check_launch("stage timing");
+    for (size_t c = 0; rc == GME_OK && c < (size_t)*calls; c++)
+        for (int s = 0; s < GME_PIPELINE_STAGES; s++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, g_timing_events[c * per + s], g_timing_events[c * per + s + 1]) != cudaSuccess) {
+                rc = check_launch("stage timing");
+                break;
+            }
+            ms_sum[s] += ms;
+        }
+    for (cudaEvent_t e : g_timing_events) cudaEventDestroy(e);
+    g_timing_events.clear();
+    return rc;
+}
+
 int gme_bbme_motion_field(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *cur, size_t cur_plane_stride,
                           int n, int H, int W, size_t pitch, int block_size, int search_window, int procedure,
                           int pnorm, int32_t *field, void *stream)
@@ -266,31 +333,39 @@ int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *c
     uint8_t *out1 = ws + L.off_out1, *out2 = ws + L.off_out2;
     int16_t *model = reinterpret_cast<int16_t *>(ws + L.off_model);
     int rc;
+    StageTimer timer(st);
+    timer.mark();
 #define GME_TRY(x) do { rc = (x); if (rc != GME_OK) return rc; } while (0)
     // utils.get_pyramids for both frames (motion.py:123-124)
     GME_TRY(launch_pyr_down(prev, pitch, prev_plane_stride, prev1, L.l1.pitch, L.l1.plane, n, H, W, st));
     GME_TRY(launch_pyr_down(cur, pitch, cur_plane_stride, cur1, L.l1.pitch, L.l1.plane, n, H, W, st));
     GME_TRY(launch_pyr_down(prev1, L.l1.pitch, L.l1.plane, prev0, L.l0.pitch, L.l0.plane, n, L.l1.H, L.l1.W, st));
     GME_TRY(launch_pyr_down(cur1, L.l1.pitch, L.l1.plane, cur0, L.l0.pitch, L.l0.plane, n, L.l1.H, L.l1.W, st));
+    timer.mark();
     // the three block-matching passes are independent of the parameters: dense L0 (motion.py:27-29),
     // then the block_size-16 fields of L1 and L2 (motion.py:224-229)
     GME_TRY(bbme_dispatch(prev0, L.l0.plane, cur0, L.l0.plane, n, L.l0.H, L.l0.W, L.l0.pitch, 2, 2, GME_SEARCH_DIAMOND,
                           GME_PNORM_MSE, dense, st));
+    timer.mark();
     GME_TRY(bbme_dispatch(prev1, L.l1.plane, cur1, L.l1.plane, n, L.l1.H, L.l1.W, L.l1.pitch, 16, search_window,
                           procedure, GME_PNORM_MSE, f1, st));
+    timer.mark();
     GME_TRY(bbme_dispatch(prev, prev_plane_stride, cur, cur_plane_stride, n, H, W, pitch, 16, search_window, procedure,
                           GME_PNORM_MSE, f2, st));
+    timer.mark();
     if (status && cudaMemsetAsync(status, 0, sizeof(int32_t) * n, st) != cudaSuccess) return check_launch("memset");
     // the sequential part: first estimate, then project + robust fit per level (motion.py:128-134)
     GME_TRY(launch_first_params(dense, n, L.R0, L.C0, params, st));
     GME_TRY(launch_affine_fit(f1, n, L.R1, L.C1, L.l1.H, L.l1.W, 0.3, 1, 1, params, out1, nullptr, nullptr, status, 1, st));
     GME_TRY(launch_affine_fit(f2, n, L.R2, L.C2, H, W, 0.3, 1, 1, params, out2, nullptr, nullptr, status, 1, st));
+    timer.mark();
     if (comp) {
         // results.py:52-59,109: model field at block_size 16, compensate previous, PSNR against current
         GME_TRY(launch_affine_field(params, n, L.R2, L.C2, model, st));
         GME_TRY(launch_compensate(prev, pitch, prev_plane_stride, model, 1, L.R2, L.C2, sse ? cur : nullptr, pitch,
                                   cur_plane_stride, comp, comp_pitch, comp_plane_stride, n, H, W, sse, st));
     }
+    timer.mark();
 #undef GME_TRY
     return GME_OK;
 }

@@ -39,6 +39,8 @@ SYMBOLS = {
     "gme_pipeline_workspace_bytes": (_sz, [_i, _i, _i]),
     "gme_pipeline": (_i, [_p, _sz, _p, _sz, _i, _i, _i, _sz, _i, _i, _p, _p, _sz, _sz, _p, _p, _p, _sz, _p]),
     "gme_pipeline_workspace_ptr": (_p, [_p, _i, _i, _i, _i]),
+    "gme_stage_timing_enable": (_i, [_i]),
+    "gme_stage_timing_read": (_i, [_p, _p]),
     "gme_launch_count": (ctypes.c_uint64, []),
 }
 
@@ -78,6 +80,22 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib.gme_launch_count())
+
+
+PIPELINE_STAGES = 6
+STAGE_NAMES = ("pyramids", "bbme_dense_l0", "bbme_l1", "bbme_l2", "fit", "compensate_psnr")
+
+
+def stage_timing_enable(on: bool) -> None:
+    check(lib.gme_stage_timing_enable(int(on)), "gme_stage_timing_enable")
+
+
+def stage_timing_read():
+    """-> (ms per stage summed over the recorded gme_pipeline calls, number of calls)."""
+    ms = (ctypes.c_double * PIPELINE_STAGES)()
+    calls = ctypes.c_int(0)
+    check(lib.gme_stage_timing_read(ms, ctypes.byref(calls)), "gme_stage_timing_read")
+    return list(ms), calls.value
 
 
 def singular_matrix_error():

@@ -131,6 +131,17 @@ GME_API int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride,
  * mask (uint8), 5 model field at full resolution (int16). */
 GME_API void *gme_pipeline_workspace_ptr(void *workspace, int n, int H, int W, int which);
 
+/* Per-stage device timing of gme_pipeline for the bench (roofline of the dominant kernel is measured
+ * live, inside the timed region).  While enabled, every gme_pipeline call records cudaEvents on its
+ * stream around its stages: 0 pyramids (4 launches), 1 dense L0 BBME, 2 L1 BBME, 3 L2 BBME, 4 first
+ * estimate + the two fits (3 launches), 5 model field + compensation + squared error (2 launches).
+ * gme_stage_timing_read synchronises on the last recorded event, adds up the elapsed milliseconds per
+ * stage over all calls since the last read into ms_sum[GME_PIPELINE_STAGES], stores the number of calls
+ * and clears the record.  Not usable while the stream is being captured into a CUDA graph. */
+#define GME_PIPELINE_STAGES 6
+GME_API int gme_stage_timing_enable(int enable);
+GME_API int gme_stage_timing_read(double *ms_sum, int *calls);
+
 /* Number of kernel launches issued through this library since load (for bench accounting). */
 GME_API uint64_t gme_launch_count(void);
 
