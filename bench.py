@@ -261,7 +261,6 @@ def main():
     del seq
     prev, cur = planes.view(0, pairs), planes.view(DISTANCE, nf)
     pipe = D.Pipeline(pairs, H, W, dev)
-    host_out = torch.empty((pairs, 8), dtype=torch.float64, pin_memory=True)    # 6 params + sse + status
     dev_out = torch.empty((pairs, 8), dtype=torch.float64, device=dev)
     flush = None if "inputs larger" in config["l2_policy"] else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     total_pairs = pairs * world
@@ -272,19 +271,23 @@ def main():
         dev_out[:, 7] = pipe.status.to(torch.float64)
         return dev_out
 
+    runner = D.HostSequenceRunner(nf, H, W, DISTANCE, chunk=max(1, pairs // 4), procedure=procedure, window=window,
+                                  device=dev)
+
     def step(e2e: bool):
         if flush is not None:
             flush.zero_()
         if e2e:
-            planes.pixels().copy_(host_frames, non_blocking=True)
+            # public host API: pinned frames in, pinned per-pair rows out; uploads overlap the kernels chunk by chunk
+            out = runner.run(host_frames)
+            if world > 1:
+                GD.gather_rows(runner.dev_rows[:, :7], total_pairs)
+            return out
         pipe.run(prev, cur, procedure, window)
         out = rows()
         if world > 1:
-            out = GD.gather_rows(out[:, :7], total_pairs)[rank * pairs:(rank + 1) * pairs]
-            if e2e:
-                host_out[:, :7].copy_(out, non_blocking=True)
-        elif e2e:
-            host_out.copy_(out, non_blocking=True)
+            GD.gather_rows(out[:, :7], total_pairs)
+        return out
 
     def barrier():
         if world > 1:
@@ -340,7 +343,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import gme_oracle as O
         fr = host_frames.numpy()
-        got = host_out.numpy().copy()
+        got = runner.host_rows.numpy().copy()
         ok = True
         for k in (0, pairs - 1):
             want = O.global_motion_estimation(fr[k], fr[k + DISTANCE], procedure=procedure, window=window)
@@ -392,8 +395,10 @@ def main():
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32 (fit: int64 sums + f64 solve)", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": nf * H * W,
-                "d2h_bytes_per_step": pairs * (7 if world > 1 else 8) * 8, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": runner.h2d_bytes,
+                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                "api": "gme_device.HostSequenceRunner.run(pinned uint8[frames,H,W]) -> pinned float64[pairs,8]",
+                "h2d_gbs": runner.h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
         "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
         "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "parity": parity,
     }

@@ -31,6 +31,8 @@ struct PatternArgs {
     int margin;        // staged margin around the tile, pixels
     int win_w, win_h;  // staged window: win_w bytes per row (multiple of 16), win_h rows
     int use_tma;
+    unsigned long long *sums;   // optional, [n][2]: per-plane sums of the two field channels (pipeline: the dense
+                                // first estimate, motion.py:186-188, is a mean -- no second pass over the field)
 };
 
 constexpr uint32_t kInfCost = 0xFFFFFFFFu;   // every real cost is < 2^32 - 1 (bs <= 255 checked on the host)
@@ -375,6 +377,7 @@ __global__ void __launch_bounds__(NT) bbme_pattern_kernel(const __grid_constant_
 
     const int group = threadIdx.x / G, ngroups = NT / G;
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
+    int sum0 = 0, sum1 = 0;
     for (int b = group; b < a.tbx * a.tby; b += ngroups) {
         const int bi = tile_r + b / a.tbx, bj = tile_c + b % a.tbx;
         if (bi >= a.R || bj >= a.C) continue;
@@ -385,6 +388,20 @@ __global__ void __launch_bounds__(NT) bbme_pattern_kernel(const __grid_constant_
         if (e.lane_g == 0) {
             int2 v = make_int2(o0, o1);
             *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = v;
+            sum0 += o0;
+            sum1 += o1;
+        }
+    }
+    if (a.sums) {
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, o);
+            sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, o);
+        }
+        if (lane == 0) {
+            if (sum0) atomicAdd(a.sums + 2 * plane, (unsigned long long)(long long)sum0);
+            if (sum1) atomicAdd(a.sums + 2 * plane + 1, (unsigned long long)(long long)sum1);
         }
     }
 }
@@ -488,6 +505,7 @@ static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
     case 16: return launch_fast<16, 16, PNORM>(a, n, stream);
     default: break;
     }
+    if (a.sums) return GME_ERR_UNSUPPORTED;              // channel sums are only produced by the tiled kernel
     const long nblocks = (long)a.R * a.C;
     const int warps = 8;
     dim3 grid((unsigned)((nblocks + warps - 1) / warps), 1, n);
@@ -498,7 +516,7 @@ static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
 
 int launch_bbme_pattern(const uint8_t *prev, size_t prev_stride, const uint8_t *cur, size_t cur_stride, int n, int H,
                         int W, size_t pitch, int bs, int sw, int procedure, int pnorm, int32_t *field,
-                        cudaStream_t stream)
+                        unsigned long long *sums, cudaStream_t stream)
 {
     PatternArgs a{};
     a.prev = prev; a.prev_stride = prev_stride;
@@ -507,6 +525,7 @@ int launch_bbme_pattern(const uint8_t *prev, size_t prev_stride, const uint8_t *
     a.R = H / bs; a.C = W / bs;
     a.sw = sw; a.procedure = procedure;
     a.field = field;
+    a.sums = sums;
     if (a.R == 0 || a.C == 0 || n == 0) return GME_OK;
     return pnorm == GME_PNORM_MAE ? launch_pattern_pn<GME_PNORM_MAE>(a, n, bs, stream)
                                   : launch_pattern_pn<GME_PNORM_MSE>(a, n, bs, stream);

@@ -13,13 +13,13 @@ namespace gme {
 
 // kernels' host launchers (one per .cu)
 int launch_bbme_pattern(const uint8_t *, size_t, const uint8_t *, size_t, int, int, int, size_t, int, int, int, int,
-                        int32_t *, cudaStream_t);
+                        int32_t *, unsigned long long *, cudaStream_t);
 int launch_bbme_exhaustive(const uint8_t *, size_t, const uint8_t *, size_t, int, int, int, size_t, int, int, int,
                            int32_t *, cudaStream_t);
 int launch_pyr_down(const uint8_t *, size_t, size_t, uint8_t *, size_t, size_t, int, int, int, cudaStream_t);
 int launch_first_params(const int32_t *, int, int, int, double *, cudaStream_t);
 int launch_affine_fit(const int32_t *, int, int, int, int, int, double, int, int, double *, uint8_t *, int32_t *,
-                      int16_t *, int32_t *, int, cudaStream_t);
+                      int16_t *, int32_t *, int, const long long *, long, cudaStream_t);
 int launch_affine_field(const double *, int, int, int, int16_t *, cudaStream_t);
 int launch_compensate(const uint8_t *, size_t, size_t, const void *, int, int, int, const uint8_t *, size_t, size_t,
                       uint8_t *, size_t, size_t, int, int, int, uint64_t *, cudaStream_t);
@@ -119,7 +119,7 @@ struct Level { int H, W; size_t pitch, plane; };
 struct Layout {
     Level l1, l0;                 // half and quarter resolution
     size_t off_prev1, off_cur1, off_prev0, off_cur0;
-    size_t off_dense, off_f1, off_f2, off_out1, off_out2, off_model, off_total;
+    size_t off_dense, off_f1, off_f2, off_out1, off_out2, off_model, off_sums, off_total;
     int R0, C0, R1, C1, R2, C2;
 };
 
@@ -137,22 +137,24 @@ static Layout make_layout(int n, int H, int W)
     L.R2 = H / 16; L.C2 = W / 16;
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
-    L.off_prev1 = take(L.l1.plane * n);
-    L.off_cur1 = take(L.l1.plane * n);
-    L.off_prev0 = take(L.l0.plane * n);
-    L.off_cur0 = take(L.l0.plane * n);
+    L.off_prev1 = take(L.l1.plane * n * 2);              // 2n planes: [prev | cur], or one run of n + d frames
+    L.off_cur1 = L.off_prev1 + L.l1.plane * n;
+    L.off_prev0 = take(L.l0.plane * n * 2);
+    L.off_cur0 = L.off_prev0 + L.l0.plane * n;
     L.off_dense = take((size_t)n * L.R0 * L.C0 * 2 * sizeof(int32_t));
     L.off_f1 = take((size_t)n * L.R1 * L.C1 * 2 * sizeof(int32_t));
     L.off_f2 = take((size_t)n * L.R2 * L.C2 * 2 * sizeof(int32_t));
     L.off_out1 = take((size_t)n * L.R1 * L.C1);
     L.off_out2 = take((size_t)n * L.R2 * L.C2);
     L.off_model = take((size_t)n * L.R2 * L.C2 * 2 * sizeof(int16_t));
+    L.off_sums = take((size_t)n * 2 * sizeof(unsigned long long));
     L.off_total = o;
     return L;
 }
 
 static int bbme_dispatch(const uint8_t *prev, size_t ps, const uint8_t *cur, size_t cs, int n, int H, int W,
-                         size_t pitch, int bs, int sw, int procedure, int pnorm, int32_t *field, cudaStream_t st)
+                         size_t pitch, int bs, int sw, int procedure, int pnorm, int32_t *field, cudaStream_t st,
+                         unsigned long long *sums = nullptr)
 {
     if (!prev || !cur || !field) return GME_ERR_INVALID_ARGUMENT;
     if (n < 0 || H <= 0 || W <= 0 || bs <= 0) return GME_ERR_INVALID_ARGUMENT;
@@ -164,7 +166,7 @@ static int bbme_dispatch(const uint8_t *prev, size_t ps, const uint8_t *cur, siz
     if (procedure == GME_SEARCH_DIAMOND && (H <= bs || W <= bs)) return GME_ERR_UNSUPPORTED;
     if (procedure == GME_SEARCH_EXHAUSTIVE)
         return launch_bbme_exhaustive(prev, ps, cur, cs, n, H, W, pitch, bs, sw, pnorm, field, st);
-    return launch_bbme_pattern(prev, ps, cur, cs, n, H, W, pitch, bs, sw, procedure, pnorm, field, st);
+    return launch_bbme_pattern(prev, ps, cur, cs, n, H, W, pitch, bs, sw, procedure, pnorm, field, sums, st);
 }
 
 }  // namespace gme
@@ -257,7 +259,7 @@ int gme_affine_fit(const int32_t *gt_field, int n, int R, int C, int level_h, in
     if (R <= 0 || C <= 0) return GME_ERR_UNSUPPORTED;   // empty field: the reference indexes an empty array
     if (n == 0) return GME_OK;
     return launch_affine_fit(gt_field, n, R, C, level_h, level_w, pct, robust, project, params, outlier, threshold,
-                             model_field, status, 0, static_cast<cudaStream_t>(stream));
+                             model_field, status, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 int gme_affine_field(const double *params, int n, int R, int C, int16_t *field, void *stream)
@@ -336,16 +338,31 @@ int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *c
     StageTimer timer(st);
     timer.mark();
 #define GME_TRY(x) do { rc = (x); if (rc != GME_OK) return rc; } while (0)
-    // utils.get_pyramids for both frames (motion.py:123-124)
-    GME_TRY(launch_pyr_down(prev, pitch, prev_plane_stride, prev1, L.l1.pitch, L.l1.plane, n, H, W, st));
-    GME_TRY(launch_pyr_down(cur, pitch, cur_plane_stride, cur1, L.l1.pitch, L.l1.plane, n, H, W, st));
-    GME_TRY(launch_pyr_down(prev1, L.l1.pitch, L.l1.plane, prev0, L.l0.pitch, L.l0.plane, n, L.l1.H, L.l1.W, st));
-    GME_TRY(launch_pyr_down(cur1, L.l1.pitch, L.l1.plane, cur0, L.l0.pitch, L.l0.plane, n, L.l1.H, L.l1.W, st));
+    // utils.get_pyramids for both frames (motion.py:123-124).  When prev and cur are two views of one
+    // sequence buffer (cur = prev + d planes, d <= n) every frame's pyramid is built once for all the pairs
+    // it belongs to, instead of once as "previous" and once as "current" -- same bytes, half the traffic.
+    const ptrdiff_t gap = cur - prev;
+    const bool sequence = cur_plane_stride == prev_plane_stride && prev_plane_stride > 0 && gap > 0 &&
+                          gap % (ptrdiff_t)prev_plane_stride == 0 && gap / (ptrdiff_t)prev_plane_stride <= n;
+    if (sequence) {
+        const int d = (int)(gap / (ptrdiff_t)prev_plane_stride);
+        cur1 = prev1 + (size_t)d * L.l1.plane;
+        cur0 = prev0 + (size_t)d * L.l0.plane;
+        GME_TRY(launch_pyr_down(prev, pitch, prev_plane_stride, prev1, L.l1.pitch, L.l1.plane, n + d, H, W, st));
+        GME_TRY(launch_pyr_down(prev1, L.l1.pitch, L.l1.plane, prev0, L.l0.pitch, L.l0.plane, n + d, L.l1.H, L.l1.W, st));
+    } else {
+        GME_TRY(launch_pyr_down(prev, pitch, prev_plane_stride, prev1, L.l1.pitch, L.l1.plane, n, H, W, st));
+        GME_TRY(launch_pyr_down(cur, pitch, cur_plane_stride, cur1, L.l1.pitch, L.l1.plane, n, H, W, st));
+        GME_TRY(launch_pyr_down(prev1, L.l1.pitch, L.l1.plane, prev0, L.l0.pitch, L.l0.plane, n, L.l1.H, L.l1.W, st));
+        GME_TRY(launch_pyr_down(cur1, L.l1.pitch, L.l1.plane, cur0, L.l0.pitch, L.l0.plane, n, L.l1.H, L.l1.W, st));
+    }
     timer.mark();
     // the three block-matching passes are independent of the parameters: dense L0 (motion.py:27-29),
     // then the block_size-16 fields of L1 and L2 (motion.py:224-229)
+    unsigned long long *sums = reinterpret_cast<unsigned long long *>(ws + L.off_sums);
+    if (cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * 2 * n, st) != cudaSuccess) return check_launch("memset");
     GME_TRY(bbme_dispatch(prev0, L.l0.plane, cur0, L.l0.plane, n, L.l0.H, L.l0.W, L.l0.pitch, 2, 2, GME_SEARCH_DIAMOND,
-                          GME_PNORM_MSE, dense, st));
+                          GME_PNORM_MSE, dense, st, sums));
     timer.mark();
     GME_TRY(bbme_dispatch(prev1, L.l1.plane, cur1, L.l1.plane, n, L.l1.H, L.l1.W, L.l1.pitch, 16, search_window,
                           procedure, GME_PNORM_MSE, f1, st));
@@ -355,9 +372,10 @@ int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *c
     timer.mark();
     if (status && cudaMemsetAsync(status, 0, sizeof(int32_t) * n, st) != cudaSuccess) return check_launch("memset");
     // the sequential part: first estimate, then project + robust fit per level (motion.py:128-134)
-    GME_TRY(launch_first_params(dense, n, L.R0, L.C0, params, st));
-    GME_TRY(launch_affine_fit(f1, n, L.R1, L.C1, L.l1.H, L.l1.W, 0.3, 1, 1, params, out1, nullptr, nullptr, status, 1, st));
-    GME_TRY(launch_affine_fit(f2, n, L.R2, L.C2, H, W, 0.3, 1, 1, params, out2, nullptr, nullptr, status, 1, st));
+    // (the first estimate -- the mean of the dense field -- is formed inside the level-1 fit from the channel sums)
+    GME_TRY(launch_affine_fit(f1, n, L.R1, L.C1, L.l1.H, L.l1.W, 0.3, 1, 1, params, out1, nullptr, nullptr, status, 1,
+                              reinterpret_cast<const long long *>(sums), (long)L.R0 * L.C0, st));
+    GME_TRY(launch_affine_fit(f2, n, L.R2, L.C2, H, W, 0.3, 1, 1, params, out2, nullptr, nullptr, status, 1, nullptr, 0, st));
     timer.mark();
     if (comp) {
         // results.py:52-59,109: model field at block_size 16, compensate previous, PSNR against current

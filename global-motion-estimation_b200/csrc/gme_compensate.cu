@@ -67,32 +67,45 @@ __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
         const uint8_t *crow = HAS_CUR ? a.cur + (size_t)plane * a.cstride + (size_t)a_row * a.cp : nullptr;
         const int npx = min(16, a.W - b0);
         const int i = a_row / a.bs, j0 = b0 / a.bs;
-        bool fast = a.vec_ok && npx == 16 && j0 == (b0 + 15) / a.bs;
+        const bool fast = a.vec_ok && npx == 16 && j0 == (b0 + 15) / a.bs;
         uint32_t px[4];
         if (fast) {
+            // branch-free gather of the 16-pixel run: aligned 32-bit loads of the source run (words that lie
+            // outside the row are not touched), funnel shift to the destination alignment, then a per-byte blend
+            // with the unmoved pixels wherever the source pixel falls outside the frame (motion.py:311-318)
+            int lo = 16, hi = 0;                                             // bytes [lo, hi) of the run are moved
+            long na = 0, s0 = 0;
             if (i < a.R && j0 < a.C) {
                 int d0, d1;
                 load_vector(a, plane, i, j0, d0, d1);
-                const long na = (long)a_row - d1, nb = (long)b0 - d0;       // motion.py:312-313
-                if (na >= 0 && na < a.H && nb >= 0 && nb + 15 < a.W) {
-                    const uint8_t *src = fplane + (size_t)na * a.fp + nb;
-                    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
-                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - mis);
-                    uint32_t r[5];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) r[k] = __ldg(sw + k);
-                    r[4] = mis ? __ldg(sw + 4) : 0u;                         // never touch a word with no wanted byte
-#pragma unroll
-                    for (int k = 0; k < 4; k++) px[k] = __funnelshift_r(r[k], r[k + 1], mis * 8);
-                } else if (na >= 0 && na < a.H && nb + 15 >= 0 && nb < a.W) {
-                    fast = false;                                            // run straddles the frame edge
-                } else {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(frow + b0);   // whole run out of frame: unchanged
-                    px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+                na = (long)a_row - d1;                                       // motion.py:312-313
+                s0 = (long)b0 - d0;
+                if (na >= 0 && na < a.H) {
+                    lo = (int)max(0L, -s0);
+                    hi = (int)min(16L, (long)a.W - s0);
                 }
-            } else {
-                const uint4 v = *reinterpret_cast<const uint4 *>(frow + b0);       // past the last whole block: copied
-                px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+            }
+            if (lo < hi) {
+                const long sa = s0 & ~3L;                                    // floor to a word boundary (also for s0 < 0)
+                const int mis = (int)(s0 - sa);
+                const uint8_t *srow = fplane + (size_t)na * a.fp;
+                uint32_t r[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const long c = sa + 4 * k;
+                    r[k] = (c >= 0 && c + 4 <= (long)a.fp && (k < 4 || mis)) ? __ldg(reinterpret_cast<const uint32_t *>(srow + c)) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) px[k] = __funnelshift_r(r[k], r[k + 1], mis * 8);
+            }
+            if (lo > 0 || hi < 16) {                                         // some pixels stay where they are
+                const uint4 v = *reinterpret_cast<const uint4 *>(frow + b0);
+                const uint32_t orig[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t m = (lo < hi) ? (byte_mask(clampi(hi - 4 * k, 0, 4)) & ~byte_mask(clampi(lo - 4 * k, 0, 4))) : 0u;
+                    px[k] = (lo < hi ? (px[k] & m) : 0u) | (orig[k] & ~m);
+                }
             }
         }
         if (fast) {

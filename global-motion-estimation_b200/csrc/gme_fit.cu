@@ -91,6 +91,9 @@ struct FitArgs {
     int16_t *model_field;
     int32_t *status;
     int status_or;   // OR into status instead of overwriting (pipeline: a singular level must stay flagged)
+    const long long *first_sums;   // pipeline: per-pair channel sums of the dense field (written by the dense
+    long first_count;              // BBME kernel); the first estimate (motion.py:186-188) is formed here
+    int cache_diffs;               // the N distances fit in dynamic shared memory
 };
 
 // 3x3 inverse the way np.linalg.inv gets it (dgesv on the identity): LU with partial pivoting,
@@ -133,24 +136,40 @@ __device__ bool inverse3(const double (&A)[3][3], double (&inv)[3][3])
     return true;
 }
 
-__global__ void __launch_bounds__(kFitThreads) affine_fit_kernel(FitArgs a)
-{
-    __shared__ long long scratch[8];
-    __shared__ unsigned int hist[2048];
-    __shared__ unsigned int chunk_sum[kFitThreads];
-    __shared__ double p[6];
-    __shared__ unsigned int sel_prefix, sel_rank;
+// One CTA of kFitBig threads per frame pair.  The field is KB-scale, so the kernel is latency-bound: the
+// distances are computed once (float64 model vector per block) and kept in shared memory for the radix
+// select and the masked sums; every block-wide step is a warp-shuffle reduction or scan.
+constexpr int kFitBig = 1024;
+constexpr int kFitWarps = kFitBig / 32;
+constexpr int kRadixBits = 11, kRadixBins = 1 << kRadixBits;
 
-    const int pair = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
+{
+    extern __shared__ __align__(16) unsigned int diff_cache[];   // [N] when a.cache_diffs
+    __shared__ long long red[kFitWarps][12];
+    __shared__ unsigned int hist[kRadixBins];
+    __shared__ unsigned int warp_tot[kFitWarps];
+    __shared__ double p[6];
+    __shared__ unsigned int sel_prefix, sel_rank, sh_dmax;
+
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long N = (long)a.R * a.C;
     const int32_t *gt = a.gt + (size_t)pair * N * 2;
     double *params = a.params + (size_t)pair * 6;
 
     if (tid < 6) {
-        double v = params[tid];
+        double v;
+        if (a.first_sums) {
+            // motion.compute_first_parameters (motion.py:186-188): float64 mean, stored as float32
+            v = (tid == 0 || tid == 3)
+                    ? (double)(float)((double)a.first_sums[2 * pair + (tid == 3)] / (double)a.first_count) : 0.0;
+        } else {
+            v = params[tid];
+        }
         if (a.project && (tid == 0 || tid == 3)) v = v * 2.0;    // motion.parameter_projection (motion.py:204-207)
         p[tid] = v;
     }
+    if (tid == 0) sh_dmax = 0;
     __syncthreads();
 
     // ---- L1 distance between the BBME field and the model field (motion.py:232-239) --------
@@ -160,6 +179,7 @@ __global__ void __launch_bounds__(kFitThreads) affine_fit_kernel(FitArgs a)
         const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * idx);
         return (unsigned int)(abs(g.x - m0) + abs(g.y - m1));
     };
+    auto diff_of = [&](long idx) -> unsigned int { return a.cache_diffs ? diff_cache[idx] : diff_at(idx); };
 
     unsigned int thr = 0xFFFFFFFFu;
     if (a.robust) {
@@ -168,56 +188,57 @@ __global__ void __launch_bounds__(kFitThreads) affine_fit_kernel(FitArgs a)
         unsigned int rank = (unsigned int)(t == 0 ? 0 : N - t);   // 0-based rank of the threshold
         unsigned int prefix = 0;                                   // bits of the answer found so far
         unsigned int dmax = 0;
-        for (long i = tid; i < N; i += kFitThreads) {
-            const unsigned int d = diff_at(i);
+        for (long i = tid; i < N; i += kFitBig) {
+            int m0, m1;
+            model_vector(p, (int)(i / a.C), (int)(i % a.C), m0, m1);
+            const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * i);
+            const unsigned int d = (unsigned int)(abs(g.x - m0) + abs(g.y - m1));
+            if (a.cache_diffs) diff_cache[i] = d;
             dmax = max(dmax, d);
-            if (a.model_field) {
-                int m0, m1;
-                model_vector(p, (int)(i / a.C), (int)(i % a.C), m0, m1);
+            if (a.model_field)
                 *reinterpret_cast<short2 *>(a.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
-            }
         }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) dmax = max(dmax, __shfl_xor_sync(0xFFFFFFFFu, dmax, o));
-        if ((tid & 31) == 0) scratch[tid >> 5] = dmax;
+        dmax = __reduce_max_sync(0xFFFFFFFFu, dmax);
+        if (lane == 0 && dmax) atomicMax(&sh_dmax, dmax);
         __syncthreads();
-        dmax = 0;
-        for (int w = 0; w < kFitThreads / 32; w++) dmax = max(dmax, (unsigned int)scratch[w]);
-        __syncthreads();
+        dmax = sh_dmax;
         // exact radix select, 11 bits per pass, starting at the highest digit that is populated
         int shift = 0;
-        while (shift + 11 < 32 && (dmax >> (shift + 11)) != 0) shift += 11;
-        for (; shift >= 0; shift -= 11) {
-            for (int i = tid; i < 2048; i += kFitThreads) hist[i] = 0;
+        while (shift + kRadixBits < 32 && (dmax >> (shift + kRadixBits)) != 0) shift += kRadixBits;
+        for (; shift >= 0; shift -= kRadixBits) {
+            for (int i = tid; i < kRadixBins; i += kFitBig) hist[i] = 0;
             __syncthreads();
-            const unsigned int hi_mask = (shift + 11 >= 32) ? 0u : (0xFFFFFFFFu << (shift + 11));
-            for (long i = tid; i < N; i += kFitThreads) {
-                const unsigned int d = diff_at(i);
-                if ((d & hi_mask) == prefix) atomicAdd(&hist[(d >> shift) & 2047u], 1u);
+            const unsigned int hi_mask = (shift + kRadixBits >= 32) ? 0u : (0xFFFFFFFFu << (shift + kRadixBits));
+            for (long i = tid; i < N; i += kFitBig) {
+                const unsigned int d = diff_of(i);
+                if ((d & hi_mask) == prefix) atomicAdd(&hist[(d >> shift) & (kRadixBins - 1)], 1u);
             }
             __syncthreads();
-            // each thread owns 8 consecutive bins; block-wide exclusive scan of the chunk sums
-            unsigned int local[8], s = 0;
+            // each thread owns 2 consecutive bins; block-wide exclusive scan of the pair sums by warp shuffles
+            const unsigned int b0 = hist[2 * tid], b1 = hist[2 * tid + 1];
+            unsigned int incl = b0 + b1;
 #pragma unroll
-            for (int k = 0; k < 8; k++) { local[k] = hist[tid * 8 + k]; s += local[k]; }
-            chunk_sum[tid] = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
             __syncthreads();
-            if (tid == 0) {
-                unsigned int run = 0;
-                for (int k = 0; k < kFitThreads; k++) { const unsigned int c = chunk_sum[k]; chunk_sum[k] = run; run += c; }
+            if (warp == 0) {
+                unsigned int v = warp_tot[lane], sc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int up = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+                    if (lane >= o) sc += up;
+                }
+                warp_tot[lane] = sc - v;                           // exclusive
             }
             __syncthreads();
-            const unsigned int before = chunk_sum[tid];
-            if (rank >= before && rank < before + s) {             // exactly one thread
-                unsigned int run = before;
-                for (int k = 0; k < 8; k++) {
-                    if (rank < run + local[k]) {
-                        sel_prefix = prefix | ((unsigned int)(tid * 8 + k) << shift);
-                        sel_rank = rank - run;
-                        break;
-                    }
-                    run += local[k];
-                }
+            const unsigned int before = warp_tot[warp] + incl - (b0 + b1);
+            if (rank >= before && rank < before + b0 + b1) {       // exactly one thread
+                const bool second = rank >= before + b0;
+                sel_prefix = prefix | ((unsigned int)(2 * tid + (second ? 1 : 0)) << shift);
+                sel_rank = rank - before - (second ? b0 : 0u);
             }
             __syncthreads();
             prefix = sel_prefix;
@@ -226,7 +247,7 @@ __global__ void __launch_bounds__(kFitThreads) affine_fit_kernel(FitArgs a)
         }
         thr = prefix;
     } else if (a.model_field) {
-        for (long i = tid; i < N; i += kFitThreads) {
+        for (long i = tid; i < N; i += kFitBig) {
             int m0, m1;
             model_vector(p, (int)(i / a.C), (int)(i % a.C), m0, m1);
             *reinterpret_cast<short2 *>(a.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
@@ -237,8 +258,8 @@ __global__ void __launch_bounds__(kFitThreads) affine_fit_kernel(FitArgs a)
     long long S[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) S[k] = 0;
-    for (long i = tid; i < N; i += kFitThreads) {
-        const bool out = a.robust ? (diff_at(i) > thr) : false;   // strict '>' (motion.py:244)
+    for (long i = tid; i < N; i += kFitBig) {
+        const bool out = a.robust ? (diff_of(i) > thr) : false;   // strict '>' (motion.py:244)
         if (a.outlier) a.outlier[(size_t)pair * N + i] = out ? 1 : 0;
         if (!out) {
             const long long x = 4 * (i / a.C), y = 4 * (i % a.C);  // motion.py:254-255
@@ -250,7 +271,21 @@ __global__ void __launch_bounds__(kFitThreads) affine_fit_kernel(FitArgs a)
         }
     }
 #pragma unroll
-    for (int k = 0; k < 12; k++) S[k] = block_sum_ll(S[k], scratch);
+    for (int k = 0; k < 12; k++) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) S[k] += __shfl_xor_sync(0xFFFFFFFFu, S[k], o);
+        if (lane == 0) red[warp][k] = S[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            long long v = red[lane][k];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            S[k] = v;
+        }
+    }
 
     if (tid == 0) {
         const double w = a.w;
@@ -287,14 +322,24 @@ int launch_first_params(const int32_t *dense, int n, int R, int C, double *param
 
 int launch_affine_fit(const int32_t *gt, int n, int R, int C, int level_h, int level_w, double pct, int robust,
                       int project, double *params, uint8_t *outlier, int32_t *threshold, int16_t *model_field,
-                      int32_t *status, int status_or, cudaStream_t stream)
+                      int32_t *status, int status_or, const long long *first_sums, long first_count,
+                      cudaStream_t stream)
 {
     FitArgs a;
     a.gt = gt; a.R = R; a.C = C;
     a.w = 1.0 / (double)((long long)level_h * level_w);
     a.pct = pct; a.robust = robust; a.project = project;
     a.params = params; a.outlier = outlier; a.threshold = threshold; a.model_field = model_field; a.status = status; a.status_or = status_or;
-    affine_fit_kernel<<<n, kFitThreads, 0, stream>>>(a);
+    a.first_sums = first_sums; a.first_count = first_count;
+    const size_t cache_bytes = (size_t)R * C * sizeof(unsigned int);
+    a.cache_diffs = (robust && cache_bytes <= 160 * 1024) ? 1 : 0;
+    const size_t smem = a.cache_diffs ? cache_bytes : 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(affine_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        configured = true;
+    }
+    affine_fit_kernel<<<n, kFitBig, smem, stream>>>(a);
     note_launch();
     return check_launch("affine_fit_kernel");
 }

@@ -4,15 +4,27 @@
 // [1 4 6 4 1] x [1 4 6 4 1], BORDER_REFLECT_101, out = (sum + 128) >> 8, output
 // ((H+1)/2, (W+1)/2).  Integer arithmetic, bit-exact against OpenCV.
 //
-// A thread produces 8 horizontally adjacent output pixels for RY consecutive output rows.
-// Per input row it issues one 128-bit load (16 pixels) plus the two neighbouring words,
-// filters horizontally on packed 16-bit pairs (two pixels per 32-bit lane op; the row sums
-// fit 12 bits and the 5x5 sum + 128 fits 16 bits, so the packed lanes never carry), and
-// keeps the five row sums of the vertical tap in a rolling register window, so every
-// input byte is read from DRAM once.
+// One CTA produces a 128 x 64 tile of the output.  Its input footprint (131 rows x 288 bytes:
+// the tile, the 2-pixel filter halo and padding to 16-byte chunks) is staged in shared memory
+// with 16-byte cp.async copies -- every input byte leaves DRAM once, in coalesced 128-bit
+// requests, without passing through registers.  Chunks that touch the frame border are filled
+// byte by byte through the reflect-101 index map instead, so the filter code never sees a
+// border.  A thread then produces 8 adjacent output pixels for 4 consecutive output rows:
+// per input row one 128-bit and two 32-bit shared loads, the horizontal tap on packed
+// 16-bit pairs (two pixels per 32-bit lane op; row sums fit 12 bits and the 5x5 sum + 128
+// fits 16 bits, so the packed lanes never carry), and a rolling window of five row sums for
+// the vertical tap.  Output rows leave as 8-byte stores, 128 bytes per 16 threads.
 #include "gme_common.cuh"
 
 namespace gme {
+
+constexpr int kPyrTileX = 128;                    // output pixels per tile row
+constexpr int kPyrTileY = 64;                     // output rows per tile
+constexpr int kPyrRY = 4;                         // output rows per thread
+constexpr int kPyrThreads = (kPyrTileX / 8) * (kPyrTileY / kPyrRY);   // 256
+constexpr int kPyrInRows = 2 * kPyrTileY + 3;     // 131
+constexpr int kPyrInPitch = 2 * kPyrTileX + 32;   // 288 bytes: 16 bytes of left padding, tile, halo, padding
+constexpr int kPyrChunks = kPyrInPitch / 16;      // 18
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
@@ -27,33 +39,24 @@ struct PyrArgs {
     uint8_t *dst;
     size_t dp, dstride;
     int H, W, Ho, Wo;
-    int vec_ok;   // src rows 16-byte aligned, dst rows 8-byte aligned
+    int vec_in;    // src rows 16-byte aligned: interior chunks travel by cp.async
+    int vec_out;   // dst rows 8-byte aligned: 8-byte stores
 };
 
-// horizontal pass for the 8 outputs whose centres are input columns ix0, ix0+2, ..., ix0+14 of (virtual) row r;
-// result: 4 registers of packed 16-bit pairs (h0,h1) (h2,h3) (h4,h5) (h6,h7)
-__device__ __forceinline__ void hrow(const PyrArgs &a, const uint8_t *plane, int r, int ix0, bool fast, uint32_t (&h)[4])
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
-    const uint8_t *row = plane + (size_t)reflect101(r, a.H) * a.sp;
-    uint32_t w[6];   // words covering columns ix0-4 .. ix0+19
-    if (fast) {
-        const uint4 m = *reinterpret_cast<const uint4 *>(row + ix0);
-        w[0] = *reinterpret_cast<const uint32_t *>(row + ix0 - 4);
-        w[1] = m.x; w[2] = m.y; w[3] = m.z; w[4] = m.w;
-        w[5] = *reinterpret_cast<const uint32_t *>(row + ix0 + 16);
-    } else {
-        // borders (reflect-101) and unaligned planes: only columns ix0-2 .. ix0+16 matter
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int col = ix0 - 4 + 4 * i + k;
-                if (col >= ix0 - 2 && col <= ix0 + 16) v |= (uint32_t)row[reflect101(col, a.W)] << (8 * k);
-            }
-            w[i] = v;
-        }
-    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// horizontal tap for the 8 outputs whose centres are tile bytes c0, c0+2, ..., c0+14 of one staged row:
+// 4 registers of packed 16-bit pairs (h0,h1) (h2,h3) (h4,h5) (h6,h7)
+__device__ __forceinline__ void hrow(const uint8_t *row, int c0, uint32_t (&h)[4])
+{
+    uint32_t w[6];   // words covering tile bytes c0-4 .. c0+19
+    const uint4 m = *reinterpret_cast<const uint4 *>(row + c0);
+    w[0] = *reinterpret_cast<const uint32_t *>(row + c0 - 4);
+    w[1] = m.x; w[2] = m.y; w[3] = m.z; w[4] = m.w;
+    w[5] = *reinterpret_cast<const uint32_t *>(row + c0 + 16);
     uint32_t e[6], o[6];   // even / odd columns of each word as 16-bit pairs
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -69,33 +72,62 @@ __device__ __forceinline__ void hrow(const PyrArgs &a, const uint8_t *plane, int
     }
 }
 
-template <int RY>
-__global__ void __launch_bounds__(256) pyr_down_kernel(PyrArgs a)
+__global__ void __launch_bounds__(kPyrThreads) pyr_down_kernel(PyrArgs a)
 {
-    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int oy0 = (blockIdx.y * blockDim.y + threadIdx.y) * RY;
-    const int ox0 = tx * 8;
-    if (ox0 >= a.Wo || oy0 >= a.Ho) return;
+    extern __shared__ __align__(16) uint8_t tile[];   // [kPyrInRows][kPyrInPitch]
+    const int ox_t = blockIdx.x * kPyrTileX, oy_t = blockIdx.y * kPyrTileY;
     const uint8_t *splane = a.src + (size_t)blockIdx.z * a.sstride;
     uint8_t *dplane = a.dst + (size_t)blockIdx.z * a.dstride;
-    const int ix0 = ox0 * 2;
-    const bool fast = a.vec_ok && ix0 >= 4 && ix0 + 20 <= a.W;
+    const int col_t = 2 * ox_t - 16;                  // image column of tile byte 0 (multiple of 16)
+    const int row_t = 2 * oy_t - 2;                   // image row of tile row 0
+    const int rows_needed = min(kPyrInRows, 2 * (a.Ho - oy_t) + 3);
+    // chunks that hold a needed byte: tile bytes 14 .. 2*valid_out + 16
+    const int last_chunk = min(kPyrChunks - 1, (2 * min(kPyrTileX, a.Wo - ox_t) + 16) / 16);
+
+    // ---- stage the input footprint -----------------------------------------------------------
+    for (int i = threadIdx.x; i < rows_needed * kPyrChunks; i += kPyrThreads) {
+        const int r = i / kPyrChunks, c = i - r * kPyrChunks;
+        if (c > last_chunk) continue;
+        const int col = col_t + 16 * c;
+        const uint8_t *srow = splane + (size_t)reflect101(row_t + r, a.H) * a.sp;
+        uint8_t *d = tile + r * kPyrInPitch + 16 * c;
+        if (a.vec_in && col >= 0 && col + 16 <= a.W) {
+            cp_async16(d, srow + col);
+        } else {
+            uint32_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                v[q] = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[q] |= (uint32_t)srow[reflect101(col + 4 * q + k, a.W)] << (8 * k);
+            }
+            *reinterpret_cast<uint4 *>(d) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- filter -------------------------------------------------------------------------------
+    const int tx = threadIdx.x % (kPyrTileX / 8), ty = threadIdx.x / (kPyrTileX / 8);
+    const int ox0 = ox_t + tx * 8, oy0 = oy_t + ty * kPyrRY;
+    if (ox0 >= a.Wo || oy0 >= a.Ho) return;
+    const int c0 = 16 + tx * 16;                      // tile byte of the first output's centre
+    const uint8_t *trow = tile + (size_t)(2 * ty * kPyrRY) * kPyrInPitch;   // tile row of image row 2*oy0 - 2
     const bool full = ox0 + 8 <= a.Wo;
 
     uint32_t hw[5][4];
-    const int r0 = 2 * oy0 - 2;
 #pragma unroll
-    for (int i = 0; i < 3; i++) hrow(a, splane, r0 + i, ix0, fast, hw[i + 2]);
+    for (int i = 0; i < 3; i++) hrow(trow + i * kPyrInPitch, c0, hw[i + 2]);
 #pragma unroll
-    for (int t = 0; t < RY; t++) {
+    for (int t = 0; t < kPyrRY; t++) {
         const int oy = oy0 + t;
         if (oy >= a.Ho) break;
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) hw[i][j] = hw[i + 2][j];
-        hrow(a, splane, 2 * oy + 1, ix0, fast, hw[3]);
-        hrow(a, splane, 2 * oy + 2, ix0, fast, hw[4]);
+        hrow(trow + (2 * t + 3) * kPyrInPitch, c0, hw[3]);
+        hrow(trow + (2 * t + 4) * kPyrInPitch, c0, hw[4]);
         uint32_t t2[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -104,7 +136,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(PyrArgs a)
         }
         const uint32_t lo = __byte_perm(t2[0], t2[1], 0x6420), hi = __byte_perm(t2[2], t2[3], 0x6420);
         uint8_t *out = dplane + (size_t)oy * a.dp + ox0;
-        if (full && a.vec_ok) {
+        if (full && a.vec_out) {
             *reinterpret_cast<uint2 *>(out) = make_uint2(lo, hi);
         } else {
             const int nvalid = min(8, a.Wo - ox0);
@@ -120,13 +152,16 @@ int launch_pyr_down(const uint8_t *src, size_t sp, size_t sstride, uint8_t *dst,
     a.src = src; a.sp = sp; a.sstride = sstride;
     a.dst = dst; a.dp = dp; a.dstride = dstride;
     a.H = H; a.W = W; a.Ho = (H + 1) / 2; a.Wo = (W + 1) / 2;
-    a.vec_ok = ((reinterpret_cast<uintptr_t>(src) | sp | sstride) % 16 == 0 &&
-                (reinterpret_cast<uintptr_t>(dst) | dp | dstride) % 8 == 0) ? 1 : 0;
-    constexpr int RY = 8;
-    dim3 block(64, 4);
-    const int tx = (a.Wo + 7) / 8, ty = (a.Ho + RY - 1) / RY;
-    dim3 grid((tx + block.x - 1) / block.x, (ty + block.y - 1) / block.y, n);
-    pyr_down_kernel<RY><<<grid, block, 0, stream>>>(a);
+    a.vec_in = ((reinterpret_cast<uintptr_t>(src) | sp | sstride) % 16 == 0) ? 1 : 0;
+    a.vec_out = ((reinterpret_cast<uintptr_t>(dst) | dp | dstride) % 8 == 0) ? 1 : 0;
+    constexpr int smem = kPyrInRows * kPyrInPitch;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(pyr_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    dim3 grid((a.Wo + kPyrTileX - 1) / kPyrTileX, (a.Ho + kPyrTileY - 1) / kPyrTileY, n);
+    pyr_down_kernel<<<grid, kPyrThreads, smem, stream>>>(a);
     note_launch();
     return check_launch("pyr_down_kernel");
 }

@@ -289,3 +289,68 @@ def gme_sequence(frames: Planes, distance: int, procedure: int = N.SEARCH_DIAMON
     pipe = pipeline or Pipeline(n, frames.H, frames.W, frames.t.device)
     pipe.run(frames.view(0, n), frames.view(distance, distance + n), procedure, window)
     return pipe
+
+
+class HostSequenceRunner:
+    """The loop of results.py:41-59,109 for a sequence that lives in HOST memory.
+
+    ``run(host_frames)`` takes pinned uint8[n_frames, H, W], returns pinned float64[n_pairs, 8] rows
+    (6 affine parameters, squared-error sum against the current frame, status) that are valid once the
+    current stream has been synchronised.  Frames travel host->device exactly once each, on a copy stream,
+    in chunk order; the pipeline of chunk j (``chunk`` pairs) starts as soon as its last frame has landed,
+    so the PCIe transfer of chunk j+1 overlaps the kernels of chunk j.  Two device sequence buffers
+    alternate between calls, so the upload of the next call overlaps the tail of this one."""
+
+    def __init__(self, n_frames: int, H: int, W: int, distance: int, chunk: int = 16,
+                 procedure: int = N.SEARCH_DIAMOND, window: int = 2, want_comp: bool = True, device=None):
+        self.device = device or require_cuda()
+        self.n_frames, self.H, self.W, self.distance = n_frames, H, W, distance
+        self.n_pairs = n_frames - distance
+        if self.n_pairs <= 0:
+            raise ValueError("sequence shorter than the frame distance")
+        self.chunk = max(1, min(chunk, self.n_pairs))
+        self.procedure, self.window = procedure, window
+        self.buffers = [Planes.empty(n_frames, H, W, self.device) for _ in range(2)]
+        self.buffer_free = [None, None]                 # event: last kernel that read the buffer has finished
+        self.turn = 0
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.pipe = Pipeline(self.chunk, H, W, self.device, want_comp)
+        tail = self.n_pairs % self.chunk
+        self.tail_pipe = Pipeline(tail, H, W, self.device, want_comp) if tail else None
+        self.dev_rows = torch.zeros((self.n_pairs, 8), dtype=torch.float64, device=self.device)
+        self.host_rows = torch.empty((self.n_pairs, 8), dtype=torch.float64, pin_memory=True)
+        self.h2d_bytes = n_frames * H * W
+        self.d2h_bytes = self.host_rows.numel() * 8
+
+    def run(self, host_frames: torch.Tensor) -> torch.Tensor:
+        if tuple(host_frames.shape) != (self.n_frames, self.H, self.W) or host_frames.dtype != torch.uint8:
+            raise ValueError("expected uint8 frames of shape [n_frames, H, W]")
+        compute = torch.cuda.current_stream(self.device)
+        planes = self.buffers[self.turn]
+        if self.buffer_free[self.turn] is not None:
+            self.copy_stream.wait_event(self.buffer_free[self.turn])
+        else:
+            self.copy_stream.wait_stream(compute)
+        uploaded = 0
+        for start in range(0, self.n_pairs, self.chunk):
+            stop = min(start + self.chunk, self.n_pairs)
+            need = stop + self.distance                  # frames [0, need) must be resident for pairs [start, stop)
+            with torch.cuda.stream(self.copy_stream):
+                planes.pixels()[uploaded:need].copy_(host_frames[uploaded:need], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(self.copy_stream)
+            uploaded = need
+            compute.wait_event(landed)
+            pipe = self.pipe if stop - start == self.chunk else self.tail_pipe
+            pipe.run(planes.view(start, stop), planes.view(start + self.distance, stop + self.distance),
+                     self.procedure, self.window)
+            rows = self.dev_rows[start:stop]
+            rows[:, :6] = pipe.params
+            rows[:, 6] = pipe.sse.to(torch.float64) if pipe.sse is not None else 0
+            rows[:, 7] = pipe.status.to(torch.float64)
+        done = torch.cuda.Event()
+        done.record(compute)
+        self.buffer_free[self.turn] = done
+        self.turn ^= 1
+        self.host_rows.copy_(self.dev_rows, non_blocking=True)
+        return self.host_rows
