@@ -37,28 +37,29 @@ __device__ __forceinline__ void load_vector(const CompArgs &a, int plane, int i,
     }
 }
 
-__device__ __forceinline__ unsigned int block_sum_u32_to_u64(unsigned int v, unsigned long long *dst)
+// per-warp partial sums -> one 64-bit atomic per CTA
+__device__ __forceinline__ void block_sum_u32_to_u64(unsigned int v, unsigned long long *dst)
 {
-    __shared__ unsigned int warp_sums[32];
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nwarps = (blockDim.x * blockDim.y + 31) / 32;
+    __shared__ unsigned int warp_sums[8];
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     if ((tid & 31) == 0) warp_sums[tid >> 5] = v;
     __syncthreads();
     if (tid == 0) {
         unsigned long long t = 0;
-        for (int w = 0; w < nwarps; w++) t += warp_sums[w];
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += warp_sums[w];
         if (t) atomicAdd(dst, t);
     }
-    return v;
 }
 
+// 16 pixels of one row per thread; block (32, 8): a warp covers 512 consecutive pixels of a row.
 template <bool HAS_CUR>
 __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
 {
     const int plane = blockIdx.z;
-    const int a_row = blockIdx.y * blockDim.y + threadIdx.y;
-    const int b0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int a_row = blockIdx.y * 8 + threadIdx.y;
+    const int b0 = (blockIdx.x * 32 + threadIdx.x) * 16;
     unsigned int err = 0;
     if (a_row < a.H && b0 < a.W) {
         const uint8_t *fplane = a.frame + (size_t)plane * a.fstride;
@@ -68,35 +69,43 @@ __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
         const int npx = min(16, a.W - b0);
         const int i = a_row / a.bs, j0 = b0 / a.bs;
         const bool fast = a.vec_ok && npx == 16 && j0 == (b0 + 15) / a.bs;
-        uint32_t px[4];
         if (fast) {
-            // branch-free gather of the 16-pixel run: aligned 32-bit loads of the source run (words that lie
-            // outside the row are not touched), funnel shift to the destination alignment, then a per-byte blend
-            // with the unmoved pixels wherever the source pixel falls outside the frame (motion.py:311-318)
+            // branch-light gather of the 16-pixel run: aligned 32-bit loads of the source run (words that lie
+            // outside the row are not touched), funnel shift to the destination alignment, then -- only for runs
+            // that straddle the frame edge -- a per-byte blend with the unmoved pixels (motion.py:311-318)
+            uint32_t px[4];
             int lo = 16, hi = 0;                                             // bytes [lo, hi) of the run are moved
-            long na = 0, s0 = 0;
+            int na = 0, s0 = 0;
             if (i < a.R && j0 < a.C) {
                 int d0, d1;
                 load_vector(a, plane, i, j0, d0, d1);
-                na = (long)a_row - d1;                                       // motion.py:312-313
-                s0 = (long)b0 - d0;
+                d0 = clampi(d0, -(1 << 24), 1 << 24);                        // any |d| >= frame size: source outside
+                d1 = clampi(d1, -(1 << 24), 1 << 24);
+                na = a_row - d1;                                             // motion.py:312-313
+                s0 = b0 - d0;
                 if (na >= 0 && na < a.H) {
-                    lo = (int)max(0L, -s0);
-                    hi = (int)min(16L, (long)a.W - s0);
+                    lo = max(0, -s0);
+                    hi = min(16, a.W - s0);
                 }
             }
             if (lo < hi) {
-                const long sa = s0 & ~3L;                                    // floor to a word boundary (also for s0 < 0)
-                const int mis = (int)(s0 - sa);
+                const int sa = s0 & ~3;                                      // floor to a word boundary (also for s0 < 0)
+                const int sh = (s0 - sa) * 8;
                 const uint8_t *srow = fplane + (size_t)na * a.fp;
                 uint32_t r[5];
+                if (sa >= 0 && sa + 20 <= (int)a.fp) {
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(srow + sa);
 #pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const long c = sa + 4 * k;
-                    r[k] = (c >= 0 && c + 4 <= (long)a.fp && (k < 4 || mis)) ? __ldg(reinterpret_cast<const uint32_t *>(srow + c)) : 0u;
+                    for (int k = 0; k < 5; k++) r[k] = __ldg(w + k);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        const int c = sa + 4 * k;
+                        r[k] = (c >= 0 && c + 4 <= (int)a.fp) ? __ldg(reinterpret_cast<const uint32_t *>(srow + c)) : 0u;
+                    }
                 }
 #pragma unroll
-                for (int k = 0; k < 4; k++) px[k] = __funnelshift_r(r[k], r[k + 1], mis * 8);
+                for (int k = 0; k < 4; k++) px[k] = __funnelshift_r(r[k], r[k + 1], sh);
             }
             if (lo > 0 || hi < 16) {                                         // some pixels stay where they are
                 const uint4 v = *reinterpret_cast<const uint4 *>(frow + b0);
@@ -107,8 +116,6 @@ __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
                     px[k] = (lo < hi ? (px[k] & m) : 0u) | (orig[k] & ~m);
                 }
             }
-        }
-        if (fast) {
             *reinterpret_cast<uint4 *>(orow + b0) = make_uint4(px[0], px[1], px[2], px[3]);
             if (HAS_CUR) {
                 const uint4 c = *reinterpret_cast<const uint4 *>(crow + b0);

@@ -49,7 +49,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 }
 
 // horizontal tap for the 8 outputs whose centres are tile bytes c0, c0+2, ..., c0+14 of one staged row:
-// 4 registers of packed 16-bit pairs (h0,h1) (h2,h3) (h4,h5) (h6,h7)
+// 4 registers of packed 16-bit pairs (h0,h1) (h2,h3) (h4,h5) (h6,h7).  Output j covers bytes
+// c0+2j-2 .. c0+2j+2: the first four taps are one IDP.4A against (1,4,6,4), the fifth is byte 0 of the next
+// word (a second IDP.4A against (1,0,0,0)); for odd j the four bytes are an aligned word, for even j they
+// straddle two words (one funnel shift).  The dot products run on the FMA pipe, the shifts on the ALU pipe.
 __device__ __forceinline__ void hrow(const uint8_t *row, int c0, uint32_t (&h)[4])
 {
     uint32_t w[6];   // words covering tile bytes c0-4 .. c0+19
@@ -57,18 +60,15 @@ __device__ __forceinline__ void hrow(const uint8_t *row, int c0, uint32_t (&h)[4
     w[0] = *reinterpret_cast<const uint32_t *>(row + c0 - 4);
     w[1] = m.x; w[2] = m.y; w[3] = m.z; w[4] = m.w;
     w[5] = *reinterpret_cast<const uint32_t *>(row + c0 + 16);
-    uint32_t e[6], o[6];   // even / odd columns of each word as 16-bit pairs
+    constexpr uint32_t kTaps = 0x04060401u, kLast = 0x00000001u;
+    uint32_t s[5];   // s[i] = bytes c0+4i-2 .. c0+4i+1
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        e[i] = w[i] & 0x00FF00FFu;
-        o[i] = (w[i] >> 8) & 0x00FF00FFu;
-    }
+    for (int i = 0; i < 5; i++) s[i] = __funnelshift_r(w[i], w[i + 1], 16);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t em = __funnelshift_r(e[j], e[j + 1], 16);       // (E[2j-1], E[2j])
-        const uint32_t ep = __funnelshift_r(e[j + 1], e[j + 2], 16);   // (E[2j+1], E[2j+2])
-        const uint32_t om = __funnelshift_r(o[j], o[j + 1], 16);       // (O[2j-1], O[2j])
-        h[j] = em + ep + 6u * e[j + 1] + 4u * (om + o[j + 1]);
+    for (int q = 0; q < 4; q++) {
+        const uint32_t even = __dp4a(s[q], kTaps, __dp4a(s[q + 1], kLast, 0u));        // output 2q: bytes c0+4q-2 ..
+        const uint32_t odd = __dp4a(w[q + 1], kTaps, __dp4a(w[q + 2], kLast, 0u));     // output 2q+1: bytes c0+4q ..
+        h[q] = even | (odd << 16);
     }
 }
 
@@ -85,15 +85,40 @@ __global__ void __launch_bounds__(kPyrThreads) pyr_down_kernel(PyrArgs a)
     const int last_chunk = min(kPyrChunks - 1, (2 * min(kPyrTileX, a.Wo - ox_t) + 16) / 16);
 
     // ---- stage the input footprint -----------------------------------------------------------
-    for (int i = threadIdx.x; i < rows_needed * kPyrChunks; i += kPyrThreads) {
-        const int r = i / kPyrChunks, c = i - r * kPyrChunks;
-        if (c > last_chunk) continue;
-        const int col = col_t + 16 * c;
-        const uint8_t *srow = splane + (size_t)reflect101(row_t + r, a.H) * a.sp;
-        uint8_t *d = tile + r * kPyrInPitch + 16 * c;
-        if (a.vec_in && col >= 0 && col + 16 <= a.W) {
-            cp_async16(d, srow + col);
-        } else {
+    // warp w copies tile rows w, w + 8, ...; lane c copies chunk c.  Chunks that overlap the frame travel whole
+    // (the row pitch is padded to 16 bytes, so a chunk that straddles column W reads padding, not foreign
+    // memory); the at most two reflect-101 columns on either side of the frame are patched in afterwards.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool generic = !a.vec_in || a.W < 32;
+    if (!generic) {
+        const int col = col_t + 16 * lane;
+        if (lane <= last_chunk && col >= 0 && col < a.W) {
+            for (int r = warp; r < rows_needed; r += kPyrThreads / 32)
+                cp_async16(tile + r * kPyrInPitch + 16 * lane, splane + (size_t)reflect101(row_t + r, a.H) * a.sp + col);
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (col_t < 0) {                                 // left frame border: columns -2, -1 mirror columns 2, 1
+            for (int r = threadIdx.x; r < rows_needed; r += kPyrThreads) {
+                uint8_t *t = tile + r * kPyrInPitch + 16;
+                t[-2] = t[2];
+                t[-1] = t[1];
+            }
+        }
+        if (col_t + kPyrInPitch > a.W) {                 // right frame border: columns W, W+1 mirror W-2, W-3
+            const int b = a.W - col_t;                   // tile byte of image column W
+            for (int r = threadIdx.x; r < rows_needed; r += kPyrThreads) {
+                uint8_t *t = tile + r * kPyrInPitch + b;
+                if (b < kPyrInPitch) t[0] = t[-2];
+                if (b + 1 < kPyrInPitch) t[1] = t[-3];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < rows_needed * kPyrChunks; i += kPyrThreads) {
+            const int r = i / kPyrChunks, c = i - r * kPyrChunks;
+            if (c > last_chunk) continue;
+            const int col = col_t + 16 * c;
+            const uint8_t *srow = splane + (size_t)reflect101(row_t + r, a.H) * a.sp;
             uint32_t v[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -101,10 +126,9 @@ __global__ void __launch_bounds__(kPyrThreads) pyr_down_kernel(PyrArgs a)
 #pragma unroll
                 for (int k = 0; k < 4; k++) v[q] |= (uint32_t)srow[reflect101(col + 4 * q + k, a.W)] << (8 * k);
             }
-            *reinterpret_cast<uint4 *>(d) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4 *>(tile + r * kPyrInPitch + 16 * c) = make_uint4(v[0], v[1], v[2], v[3]);
         }
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ---- filter -------------------------------------------------------------------------------
