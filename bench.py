@@ -176,19 +176,74 @@ def host_cores() -> int:
 
 
 # ----------------------------------------------------------------------------------------------
-def algorithmic_bytes_per_pair(H, W):
-    """bytes each stage must move per frame pair (uint8 pixels, int32 fields)."""
+def algorithmic_bytes_per_step(H, W, pairs, frames):
+    """bytes each stage must move per step (uint8 pixels, int32 fields).  The pyramids are built
+    once per FRAME of the sequence (each frame serves as `previous` of one pair and `current` of another), so
+    they are counted at 1.5625*H*W per frame, not 3.125*H*W per pair as the reference does it."""
     H1, W1 = (H + 1) // 2, (W + 1) // 2
     H0, W0 = (H1 + 1) // 2, (W1 + 1) // 2
     nb0, nb1, nb2 = (H0 // 2) * (W0 // 2), (H1 // 16) * (W1 // 16), (H // 16) * (W // 16)
     return {
-        "pyramids": 2 * (H * W + 2 * H1 * W1 + H0 * W0),            # both frames: read L2, write+read L1, write L0
-        "bbme_dense_l0": 2 * H0 * W0 + 8 * nb0,
-        "bbme_l1": 2 * H1 * W1 + 8 * nb1,
-        "bbme_l2": 2 * H * W + 8 * nb2,
-        "fit": 8 * (nb0 + nb1 + nb2) + nb1 + nb2 + 48,
-        "compensate_psnr": 3 * H * W + 4 * nb2,
+        "pyramids": frames * (H * W + 2 * H1 * W1 + H0 * W0),       # read L2, write + read L1, write L0
+        "bbme_dense_l0": pairs * (2 * H0 * W0 + 8 * nb0),
+        "bbme_l1": pairs * (2 * H1 * W1 + 8 * nb1),
+        "bbme_l2": pairs * (2 * H * W + 8 * nb2),
+        "fit": pairs * (8 * (nb1 + nb2) + nb1 + nb2 + 48),
+        "compensate_psnr": pairs * (3 * H * W + 4 * nb2),
     }
+
+
+def exhaustive_ops(H, W, bs, sw):
+    """pixel-pair operations of one exhaustive search = sum over blocks of nv_r * nv_c * bs^2, with
+    nv(p) = min(p + sw + bs - 1, N - bs) - max(p - sw, 0) + 1 the in-frame offsets along one axis."""
+    def nv(p, n):
+        return min(p + sw + bs - 1, n - bs) - max(p - sw, 0) + 1
+    rows = sum(nv(r, H) for r in range(0, H - bs + 1, bs))
+    cols = sum(nv(c, W) for c in range(0, W - bs + 1, bs))
+    return rows * cols * bs * bs
+
+
+def bench_exhaustive(D, N, torch, planes, dev):
+    """BBME SAD Gop/s vs the integer-pipe roofline (BASELINE.json metric, second half): the exhaustive kernel on
+    config-1 and config-5 shaped inputs, against the rate of its own instruction mix measured by the probe."""
+    import ctypes
+    out = {}
+    scratch = torch.zeros(1024, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / reps
+
+    peaks = {}
+    for pn, name in ((0, "sad"), (1, "ssd")):
+        npix = ctypes.c_uint64(0)
+        t = timed(lambda: N.check(N.lib.gme_sad_peak_probe(pn, 148 * 16, 2048, scratch.data_ptr(), ctypes.byref(npix), stream)), 5)
+        peaks[pn] = npix.value / t
+        out[f"probe_{name}_tops"] = peaks[pn] / 1e12
+    H, W = planes.H, planes.W
+    cases = [("cfg1_mae_bs12_sw12_320x240_x256", 240, 320, 12, 12, 0, 256), ("cfg5_mse_bs16_sw32_%dx%d_x4" % (W, H), H, W, 16, 32, 1, 4)]
+    for name, h, w, bs, sw, pn, n in cases:
+        if h == H and w == W:
+            prev, cur = planes.view(0, n), planes.view(DISTANCE, DISTANCE + n)
+        else:
+            crop = D.Planes.empty(n + DISTANCE, h, w, dev)
+            src = planes.pixels()
+            for k in range(n + DISTANCE):
+                crop.pixels()[k].copy_(src[k % src.shape[0], 100:100 + h, 200:200 + w])
+            prev, cur = crop.view(0, n), crop.view(DISTANCE, DISTANCE + n)
+        t = timed(lambda: D.motion_field(prev, cur, bs, sw, 0, pn), 5)
+        ops = exhaustive_ops(h, w, bs, sw) * n
+        out[name] = {"tops": ops / t / 1e12, "ms": t * 1e3, "pixel_pair_ops": ops, "frac_of_probe_peak": ops / t / peaks[pn]}
+    return out
 
 
 def main():
@@ -361,11 +416,11 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    bytes_pp = algorithmic_bytes_per_pair(H, W)
+    bytes_ps = algorithmic_bytes_per_step(H, W, pairs, nf)
     stages = {}
     for name, ms in zip(N.STAGE_NAMES, stage_ms):
         per_call = ms / args.steps
-        gbs = bytes_pp[name] * pairs / (per_call * 1e-3) / 1e9 if per_call > 0 else 0.0
+        gbs = bytes_ps[name] / (per_call * 1e-3) / 1e9 if per_call > 0 else 0.0
         stages[name] = {"ms_per_step": per_call, "share": ms / max(sum(stage_ms), 1e-12), "algorithmic_gbs": gbs,
                         "frac_of_hbm_peak": gbs / hbm_peak}
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
@@ -376,8 +431,13 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["algorithmic_gbs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": stages[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_pp[dom] * pairs,
-                "whole_step_algorithmic_gbs": sum(bytes_pp.values()) * pairs / (ms_total / args.steps * 1e-3) / 1e9}
+                "algorithmic_bytes_per_launch": bytes_ps[dom],
+                "whole_step_algorithmic_gbs": sum(bytes_ps.values()) / (ms_total / args.steps * 1e-3) / 1e9}
+    exhaustive = None
+    try:
+        exhaustive = bench_exhaustive(D, N, torch, planes, dev)
+    except Exception as exc:                                                      # noqa: BLE001
+        exhaustive = {"error": str(exc)}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -400,7 +460,8 @@ def main():
                 "api": "gme_device.HostSequenceRunner.run(pinned uint8[frames,H,W]) -> pinned float64[pairs,8]",
                 "h2d_gbs": runner.h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
         "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-        "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "parity": parity,
+        "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "bbme_exhaustive": exhaustive,
+        "cpu_baseline": cpu, "parity": parity,
     }
     print(json.dumps(out))
     if world > 1:

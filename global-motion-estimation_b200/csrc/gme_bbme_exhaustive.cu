@@ -264,6 +264,43 @@ static int launch_exhaustive_pn(ExhaustiveArgs a, int n, int bs, cudaStream_t st
     return check_launch("bbme_exhaustive_generic_kernel");
 }
 
+// ---------------------------------------------------------------------------------------
+// Integer-pipe probe: the roofline denominator of the exhaustive search.  Every thread runs `iters` rounds of
+// eight independent packed cost updates (VABSDIFF4.ACC for SAD, VABSDIFF4 + IDP.4A for SSD) on registers --
+// no memory traffic -- so elapsed time gives the sustained pixel-pair rate of the instruction mix itself.
+// ---------------------------------------------------------------------------------------
+template <int PNORM>
+__global__ void __launch_bounds__(256) sad_probe_kernel(uint32_t seed, int iters, uint32_t *out)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = (tid + 1u) * 2654435761u + k * 0x9E3779B9u + seed; acc[k] = 0; }
+    uint32_t b = seed ^ (tid * 0x85EBCA6Bu);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = cost4_acc<PNORM>(a[k], b, acc[k]);
+            b = __funnelshift_l(b, b, 5) ^ a[r];
+        }
+    }
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t ^= acc[k];
+    if (t == 0x12345678u) out[tid & 1023] = t;          // keeps the chain alive; practically never taken
+}
+
+int launch_sad_probe(int pnorm, int ctas, int iters, uint32_t *out, cudaStream_t stream)
+{
+    if (pnorm == GME_PNORM_MAE)
+        sad_probe_kernel<GME_PNORM_MAE><<<ctas, 256, 0, stream>>>(12345u, iters, out);
+    else
+        sad_probe_kernel<GME_PNORM_MSE><<<ctas, 256, 0, stream>>>(12345u, iters, out);
+    note_launch();
+    return check_launch("sad_probe_kernel");
+}
+
 int launch_bbme_exhaustive(const uint8_t *prev, size_t prev_stride, const uint8_t *cur, size_t cur_stride, int n,
                            int H, int W, size_t pitch, int bs, int sw, int pnorm, int32_t *field, cudaStream_t stream)
 {

@@ -16,6 +16,7 @@ int launch_bbme_pattern(const uint8_t *, size_t, const uint8_t *, size_t, int, i
                         int32_t *, unsigned long long *, cudaStream_t);
 int launch_bbme_exhaustive(const uint8_t *, size_t, const uint8_t *, size_t, int, int, int, size_t, int, int, int,
                            int32_t *, cudaStream_t);
+int launch_sad_probe(int, int, int, uint32_t *, cudaStream_t);
 int launch_pyr_down(const uint8_t *, size_t, size_t, uint8_t *, size_t, size_t, int, int, int, cudaStream_t);
 int launch_first_params(const int32_t *, int, int, int, double *, cudaStream_t);
 int launch_affine_fit(const int32_t *, int, int, int, int, int, double, int, int, double *, uint8_t *, int32_t *,
@@ -193,6 +194,13 @@ const char *gme_error_string(int code)
 int gme_last_cuda_error(void) { return g_last_cuda_error.load(); }
 
 uint64_t gme_launch_count(void) { return g_launches.load(); }
+
+int gme_sad_peak_probe(int pnorm, int ctas, int iters, uint32_t *scratch, uint64_t *pixel_pairs, void *stream)
+{
+    if (!scratch || !pixel_pairs || ctas <= 0 || iters <= 0 || pnorm < 0 || pnorm > 1) return GME_ERR_INVALID_ARGUMENT;
+    *pixel_pairs = (uint64_t)ctas * 256u * (uint64_t)iters * 4u * 8u * 4u;   // threads x rounds x 8 updates x 4 pixels
+    return launch_sad_probe(pnorm, ctas, iters, scratch, static_cast<cudaStream_t>(stream));
+}
 
 int gme_stage_timing_enable(int enable)
 {

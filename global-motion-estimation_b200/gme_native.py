@@ -41,6 +41,7 @@ SYMBOLS = {
     "gme_pipeline_workspace_ptr": (_p, [_p, _i, _i, _i, _i]),
     "gme_stage_timing_enable": (_i, [_i]),
     "gme_stage_timing_read": (_i, [_p, _p]),
+    "gme_sad_peak_probe": (_i, [_i, _i, _i, _p, _p, _p]),
     "gme_launch_count": (ctypes.c_uint64, []),
 }
 

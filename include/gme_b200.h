@@ -142,6 +142,12 @@ GME_API void *gme_pipeline_workspace_ptr(void *workspace, int n, int H, int W, i
 GME_API int gme_stage_timing_enable(int enable);
 GME_API int gme_stage_timing_read(double *ms_sum, int *calls);
 
+/* Roofline denominator of the exhaustive search (bench only): runs the search's packed cost instruction mix
+ * (pnorm 0: VABSDIFF4.ACC, 1: VABSDIFF4 + IDP.4A) on registers, ctas x 256 threads x iters rounds, and stores
+ * the number of pixel-pair updates issued in *pixel_pairs (host).  scratch: >= 1024 uint32 on the device.
+ * Time it with events: pixel_pairs / elapsed = sustained integer-pipe peak for that norm. */
+GME_API int gme_sad_peak_probe(int pnorm, int ctas, int iters, uint32_t *scratch, uint64_t *pixel_pairs, void *stream);
+
 /* Number of kernel launches issued through this library since load (for bench accounting). */
 GME_API uint64_t gme_launch_count(void);
 
