@@ -13,6 +13,8 @@
 // Scan orders, strict '<' first-minimum tie-breaking, the diamond clamp to H-bs-1, the
 // swapped SDSP offsets, the double-counted three-step offset and the unbounded 2D-log walk
 // are reproduced exactly; the oracle is oracle/gme_oracle.c.
+#include <cstdlib>
+
 #include "gme_common.cuh"
 
 namespace gme {
@@ -407,6 +409,284 @@ __global__ void __launch_bounds__(NT) bbme_pattern_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------
+// Diamond search on 16 x 16 macroblocks -- the search the GME pipeline runs on L1 and L2
+// (motion.py:224-229), i.e. the dominant kernel of the whole path.
+//
+// One warp per macroblock.  The nine LDSP candidates of a step all lie in the 20 x 20 pixel
+// neighbourhood of the current centre, so that neighbourhood is loaded from the staged window
+// ONCE per step into registers (lane R < 20 owns its row R: two LDS.128 + one LDS.32,
+// byte-aligned with funnel shifts) instead of once per candidate; lane R scores its row against
+// the anchor rows R-2-dr it holds in registers (five rows, loaded once per macroblock) and a
+// candidate's cost is one REDUX.SUM over the warp.  Everything that steers the walk (alignment,
+// costs, the chosen direction) is warp-uniform, so the control flow never diverges.
+// A step re-evaluates only the candidates the previous step has not already scored: the cost
+// of a position does not depend on the step that asks for it, so reusing it is exact, and the
+// strict-'<' scan over the nine costs in the reference's order keeps the tie-breaking.
+// The final SDSP reuses the registers of the last LDSP step (same centre).  Whenever the
+// clamp of bbme.py:503-504 could act (centre within 2 pixels of its bounds) or the
+// neighbourhood leaves the staged window, the step falls back to the candidate-at-a-time
+// evaluator above (BlockEval<16, 32>), which handles clamped and far-away positions.
+// ---------------------------------------------------------------------------------------
+template <int PNORM, int NT>
+__global__ void __launch_bounds__(NT) bbme_diamond16_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
+{
+    constexpr int BS = 16;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+
+    const int plane = blockIdx.z;
+    const int tile_r = blockIdx.y * a.tby, tile_c = blockIdx.x * a.tbx;
+    const int wr0 = tile_r * BS - a.margin, wc0 = (tile_c * BS - a.margin) & ~15;
+    const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
+    const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
+
+    stage_window(smem, &bar, &cur_map, a.use_tma, cur_plane, plane, a.H, a.W, a.pitch, wr0, wc0, a.win_w, a.win_h);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);   // tells the compiler it is warp-uniform
+    BlockEval<BS, 32, PNORM> e;                       // fallback evaluator: 32 lanes share one candidate
+    e.cur_plane = cur_plane;
+    e.win = reinterpret_cast<const uint32_t *>(smem);
+    e.pitch = a.pitch;
+    e.win_pw = a.win_w / 4;
+    e.wr0 = wr0;
+    e.wc0 = wc0;
+    e.wr1 = wr0 + a.win_h;
+    e.wc1 = wc0 + a.win_w - 4;
+    e.lane_g = lane;
+    e.gmask = 0xFFFFFFFFu;
+
+    constexpr int LR[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};      // LDSP offsets (row, col), bbme.py:463-472
+    constexpr int LC[9] = {0, 0, 1, 2, 1, 0, -1, -2, -1};
+    constexpr int SR[5] = {0, 0, 1, 0, -1};                    // SDSP as applied (swapped), bbme.py:474-480,518-521
+    constexpr int SC[5] = {0, 1, 0, -1, 0};
+    // the same tables as nibbles (value + 2), for lookups by a run-time index without a local-memory array
+    constexpr unsigned long long LRP = 0x321012342ull, LCP = 0x101234322ull;
+    constexpr unsigned SRP = 0x12322u, SCP = 0x21232u;
+    const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
+    // centres for which the register path applies: no clamp can act on the 5 x 5 neighbourhood of offsets, and the
+    // 20 x 20 pixel neighbourhood (read as 36 bytes from a 16-byte boundary) lies inside the staged window
+    const int fr_lo = max(2, wr0 + 2), fr_hi = min(rmax - 2, wr0 + a.win_h - 18);
+    const int fc_lo = max(2, wc0 + 2), fc_hi = min(cmax - 2, wc0 + 2 + a.win_w - 36);
+    const int Rl = min(lane, 19);                              // neighbourhood row this lane loads
+    const bool prev_vec = ((reinterpret_cast<uintptr_t>(a.prev) | a.pitch | a.prev_stride) & 15) == 0;
+    int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
+
+    for (int b = warp; b < a.tbx * a.tby; b += NT / 32) {
+        const int bi = tile_r + b / a.tbx, bj = tile_c + b % a.tbx;
+        if (bi >= a.R || bj >= a.C) continue;
+        const int br = bi * BS, bc = bj * BS;
+
+        // anchor rows for the register path: anc[d] = anchor row lane - d, scored when a candidate has dr = d - 2;
+        // msk[d] zeroes the contribution of lanes whose row lies outside that candidate
+        uint32_t anc[5][4], msk[5];
+#pragma unroll
+        for (int d = 0; d < 5; d++) {
+            const int k = lane - d;
+            const bool ok = lane < 20 && k >= 0 && k < BS;
+            const uint8_t *p = prev_plane + (size_t)(br + (ok ? k : 0)) * a.pitch + bc;
+            if (prev_vec) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+                anc[d][0] = v.x; anc[d][1] = v.y; anc[d][2] = v.z; anc[d][3] = v.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    anc[d][i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
+                                ((uint32_t)p[4 * i + 3] << 24);
+            }
+            msk[d] = ok ? 0xFFFFFFFFu : 0u;
+        }
+
+        uint32_t z[5] = {0, 0, 0, 0, 0};   // bytes 0..19 of this lane's neighbourhood row; byte 0 = image column mc - 2
+        auto load_region = [&](int mr, int mc) {
+            const int xs = mc - 2 - wc0;
+            const int o = xs & 15;
+            const uint8_t *p = smem + (mr - 2 - wr0 + Rl) * a.win_w + (xs & ~15);
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(p), q1 = *reinterpret_cast<const uint4 *>(p + 16);
+            const uint32_t v8 = *reinterpret_cast<const uint32_t *>(p + 32);
+            uint32_t u[6];
+            switch (o >> 2) {              // warp-uniform
+            case 0: u[0] = q0.x; u[1] = q0.y; u[2] = q0.z; u[3] = q0.w; u[4] = q1.x; u[5] = q1.y; break;
+            case 1: u[0] = q0.y; u[1] = q0.z; u[2] = q0.w; u[3] = q1.x; u[4] = q1.y; u[5] = q1.z; break;
+            case 2: u[0] = q0.z; u[1] = q0.w; u[2] = q1.x; u[3] = q1.y; u[4] = q1.z; u[5] = q1.w; break;
+            default: u[0] = q0.w; u[1] = q1.x; u[2] = q1.y; u[3] = q1.z; u[4] = q1.w; u[5] = v8; break;
+            }
+            const int bsh = (o & 3) * 8;
+#pragma unroll
+            for (int i = 0; i < 5; i++) z[i] = __funnelshift_r(u[i], u[i + 1], bsh);
+        };
+        // cost of the candidate at column offset dc (the shifted words s) and row offset dr = d - 2
+        auto cand = [&](const uint32_t (&s)[4], int d) -> uint32_t {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc = cost4_acc<PNORM>(s[i], anc[d][i], acc);
+            return __reduce_add_sync(0xFFFFFFFFu, acc & msk[d]);
+        };
+        auto shifted = [&](int bits, uint32_t (&s)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) s[i] = __funnelshift_r(z[i], z[i + 1], bits);
+        };
+
+        int mr = br, mc = bc;
+        uint32_t c[9];
+        bool have = false, last_fast = false;     // have: c[] are the costs around the previous centre, which moved by L[kb]
+        int kb = 0;
+        for (;;) {                                                 // LDSP, bbme.py:494-513
+            if (mr >= fr_lo && mr <= fr_hi && mc >= fc_lo && mc <= fc_hi) {
+                load_region(mr, mc);
+                if (!have) {
+                    uint32_t s[4];
+                    shifted(16, s);
+                    c[0] = cand(s, 2); c[1] = cand(s, 4); c[5] = cand(s, 0);
+                    shifted(24, s);
+                    c[2] = cand(s, 3); c[4] = cand(s, 1);
+                    shifted(8, s);
+                    c[6] = cand(s, 1); c[8] = cand(s, 3);
+                    { const uint32_t t[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(t, 2); }
+                    { const uint32_t t[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(t, 2); }
+                } else {
+                    // only the candidates the previous step has not scored; the others keep their cost (exact: the
+                    // cost of a position does not depend on which step asks for it)
+                    switch (kb) {
+                    case 1: {                                       // centre moved by (2, 0)
+                        const uint32_t n0 = c[1]; const uint32_t n4 = c[2]; const uint32_t n5 = c[0]; const uint32_t n6 = c[8];
+                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
+                        { uint32_t s[4]; shifted(8, s); c[8] = cand(s, 3); }
+                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); }
+                        { uint32_t s[4]; shifted(24, s); c[2] = cand(s, 3); }
+                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
+                        c[0] = n0; c[4] = n4; c[5] = n5; c[6] = n6;
+                        break;
+                    }
+                            case 2: {                                       // centre moved by (1, 1)
+                        const uint32_t n0 = c[2]; const uint32_t n4 = c[3]; const uint32_t n5 = c[4]; const uint32_t n6 = c[0]; const uint32_t n7 = c[8]; const uint32_t n8 = c[1];
+                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); }
+                        { uint32_t s[4]; shifted(24, s); c[2] = cand(s, 3); }
+                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
+                        c[0] = n0; c[4] = n4; c[5] = n5; c[6] = n6; c[7] = n7; c[8] = n8;
+                        break;
+                    }
+                            case 3: {                                       // centre moved by (0, 2)
+                        const uint32_t n0 = c[3]; const uint32_t n6 = c[4]; const uint32_t n7 = c[0]; const uint32_t n8 = c[2];
+                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); c[5] = cand(s, 0); }
+                        { uint32_t s[4]; shifted(24, s); c[2] = cand(s, 3); c[4] = cand(s, 1); }
+                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
+                        c[0] = n0; c[6] = n6; c[7] = n7; c[8] = n8;
+                        break;
+                    }
+                            case 4: {                                       // centre moved by (-1, 1)
+                        const uint32_t n0 = c[4]; const uint32_t n1 = c[2]; const uint32_t n2 = c[3]; const uint32_t n6 = c[5]; const uint32_t n7 = c[6]; const uint32_t n8 = c[0];
+                        { uint32_t s[4]; shifted(16, s); c[5] = cand(s, 0); }
+                        { uint32_t s[4]; shifted(24, s); c[4] = cand(s, 1); }
+                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
+                        c[0] = n0; c[1] = n1; c[2] = n2; c[6] = n6; c[7] = n7; c[8] = n8;
+                        break;
+                    }
+                            case 5: {                                       // centre moved by (-2, 0)
+                        const uint32_t n0 = c[5]; const uint32_t n1 = c[0]; const uint32_t n2 = c[4]; const uint32_t n8 = c[6];
+                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
+                        { uint32_t s[4]; shifted(8, s); c[6] = cand(s, 1); }
+                        { uint32_t s[4]; shifted(16, s); c[5] = cand(s, 0); }
+                        { uint32_t s[4]; shifted(24, s); c[4] = cand(s, 1); }
+                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
+                        c[0] = n0; c[1] = n1; c[2] = n2; c[8] = n8;
+                        break;
+                    }
+                            case 6: {                                       // centre moved by (-1, -1)
+                        const uint32_t n0 = c[6]; const uint32_t n1 = c[8]; const uint32_t n2 = c[0]; const uint32_t n3 = c[4]; const uint32_t n4 = c[5]; const uint32_t n8 = c[7];
+                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
+                        { uint32_t s[4]; shifted(8, s); c[6] = cand(s, 1); }
+                        { uint32_t s[4]; shifted(16, s); c[5] = cand(s, 0); }
+                        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3; c[4] = n4; c[8] = n8;
+                        break;
+                    }
+                            case 7: {                                       // centre moved by (0, -2)
+                        const uint32_t n0 = c[7]; const uint32_t n2 = c[8]; const uint32_t n3 = c[0]; const uint32_t n4 = c[6];
+                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
+                        { uint32_t s[4]; shifted(8, s); c[6] = cand(s, 1); c[8] = cand(s, 3); }
+                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); c[5] = cand(s, 0); }
+                        c[0] = n0; c[2] = n2; c[3] = n3; c[4] = n4;
+                        break;
+                    }
+                            case 8: {                                       // centre moved by (1, -1)
+                        const uint32_t n0 = c[8]; const uint32_t n2 = c[1]; const uint32_t n3 = c[2]; const uint32_t n4 = c[0]; const uint32_t n5 = c[6]; const uint32_t n6 = c[7];
+                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
+                        { uint32_t s[4]; shifted(8, s); c[8] = cand(s, 3); }
+                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); }
+                        c[0] = n0; c[2] = n2; c[3] = n3; c[4] = n4; c[5] = n5; c[6] = n6;
+                        break;
+                    }
+                    default: break;
+                    }
+                }
+                // first strict minimum in candidate order (bbme.py:506-510): costs < 2^24, so (cost, index) packs in 32 bits
+                uint32_t key = c[0] << 4;
+#pragma unroll
+                for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
+                kb = (int)(key & 15u);
+                if (kb == 0) { last_fast = true; break; }          // the centre wins: positions are distinct here
+                mr += (int)((LRP >> (4 * kb)) & 15) - 2;
+                mc += (int)((LCP >> (4 * kb)) & 15) - 2;
+                have = true;
+            } else {
+                e.load_anchor(prev_plane, br, bc);
+                int r[9], cc[9];
+                uint32_t cost[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    r[k] = clampi(mr + LR[k], 0, rmax);
+                    cc[k] = clampi(mc + LC[k], 0, cmax);
+                }
+                e.template eval<9>(r, cc, cost);
+                uint32_t best = kInfCost;
+                int best_r = mr, best_c = mc;
+#pragma unroll
+                for (int k = 0; k < 9; k++)
+                    if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = cc[k]; }
+                have = false;
+                if (best_r == mr && best_c == mc) { last_fast = false; break; }
+                mr = best_r;
+                mc = best_c;
+            }
+        }
+
+        int out_r, out_c;
+        if (last_fast) {                                           // SDSP on the registers of the last step
+            uint32_t s0[4], sp[4], sm[4];
+            shifted(16, s0);
+            shifted(24, sp);
+            shifted(8, sm);
+            uint32_t key = c[0] << 4;
+            key = min(key, (cand(sp, 2) << 4) | 1u);               // (0, +1)
+            key = min(key, (cand(s0, 3) << 4) | 2u);               // (+1, 0)
+            key = min(key, (cand(sm, 2) << 4) | 3u);               // (0, -1)
+            key = min(key, (cand(s0, 1) << 4) | 4u);               // (-1, 0)
+            const int ks = (int)(key & 15u);
+            out_r = mr + (int)((SRP >> (4 * ks)) & 15) - 2;
+            out_c = mc + (int)((SCP >> (4 * ks)) & 15) - 2;
+        } else {
+            e.load_anchor(prev_plane, br, bc);
+            int r[5], cc[5];
+            uint32_t cost[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                r[k] = clampi(mr + SR[k], 0, rmax);
+                cc[k] = clampi(mc + SC[k], 0, cmax);
+            }
+            e.template eval<5>(r, cc, cost);
+            uint32_t best = kInfCost;
+            out_r = mr;
+            out_c = mc;
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (cost[k] < best) { best = cost[k]; out_r = r[k]; out_c = cc[k]; }
+        }
+        if (lane == 0)
+            *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(out_c - bc, out_r - br);   // bbme.py:531-532
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Generic path: any block size 1..255, a full warp per macroblock, global memory only.
 // ---------------------------------------------------------------------------------------
 template <int PNORM>
@@ -495,8 +775,32 @@ static int launch_fast(PatternArgs a, int n, cudaStream_t stream)
 }
 
 template <int PNORM>
+static int launch_diamond16(PatternArgs a, int n, cudaStream_t stream)
+{
+    constexpr int NT = 256, BS = 16;
+    const int tbx = min(8, a.C), tby = min(4, a.R);
+    const int margin = 32;
+    int win_w = tbx * BS + 2 * margin + 4 + 15;          // as launch_fast: funnel slack + 16-byte rounding of column 0
+    win_w = (win_w + 15) / 16 * 16;
+    const int win_h = tby * BS + 2 * margin;
+    a.tbx = tbx; a.tby = tby; a.margin = margin; a.win_w = win_w; a.win_h = win_h;
+    CUtensorMap map;
+    a.use_tma = make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h) ? 1 : 0;
+    if (!a.use_tma) memset(&map, 0, sizeof(map));
+    const size_t smem = (size_t)win_w * win_h + 64;      // slack: the register path reads 36 bytes from a 16-byte boundary
+    auto kern = bbme_diamond16_kernel<PNORM, NT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
+    kern<<<grid, NT, smem, stream>>>(map, a);
+    note_launch();
+    return check_launch("bbme_diamond16_kernel");
+}
+
+template <int PNORM>
 static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
 {
+    if (bs == 16 && a.procedure == GME_SEARCH_DIAMOND && !a.sums && getenv("GME_DIAMOND16_OLD") == nullptr)
+        return launch_diamond16<PNORM>(a, n, stream);
     switch (bs) {
     case 2: return launch_fast<2, 1, PNORM>(a, n, stream);
     case 4: return launch_fast<4, 1, PNORM>(a, n, stream);
