@@ -428,19 +428,52 @@ __global__ void __launch_bounds__(NT) bbme_pattern_kernel(const __grid_constant_
 // evaluator above (BlockEval<16, 32>), which handles clamped and far-away positions.
 // ---------------------------------------------------------------------------------------
 template <int PNORM, int NT>
-__global__ void __launch_bounds__(NT) bbme_diamond16_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
+__global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_constant__ CUtensorMap cur_map,
+                                                                      const __grid_constant__ CUtensorMap prev_map, PatternArgs a)
 {
     constexpr int BS = 16;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
 
     const int plane = blockIdx.z;
-    const int tile_r = blockIdx.y * a.tby, tile_c = blockIdx.x * a.tbx;
+    constexpr int TBX = 8, TBY = 4;                   // macroblocks per tile (fixed: index math by shifts)
+    const int tile_r = blockIdx.y * TBY, tile_c = blockIdx.x * TBX;
     const int wr0 = tile_r * BS - a.margin, wc0 = (tile_c * BS - a.margin) & ~15;
     const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
     const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
 
-    stage_window(smem, &bar, &cur_map, a.use_tma, cur_plane, plane, a.H, a.W, a.pitch, wr0, wc0, a.win_w, a.win_h);
+    // the tile's anchor blocks (128 x 64 pixels of `previous`) are staged too, 144 bytes per row so that the
+    // 128-bit row loads of consecutive lanes fall into different banks
+    constexpr int APITCH = 144;
+    uint8_t *anchors = smem + (((size_t)a.win_w * a.win_h + 64 + 127) & ~(size_t)127);
+    if (a.use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&bar, (uint32_t)(a.win_w * a.win_h + APITCH * TBY * BS));
+            tma_load_3d(smem, &cur_map, &bar, wc0, wr0, plane);
+            tma_load_3d(anchors, &prev_map, &bar, tile_c * BS, tile_r * BS, plane);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        stage_window(smem, &bar, &cur_map, 0, cur_plane, plane, a.H, a.W, a.pitch, wr0, wc0, a.win_w, a.win_h);
+        for (int i = threadIdx.x; i < TBY * BS * (TBX * BS / 4); i += NT) {
+            const int r = i / (TBX * BS / 4), w = i % (TBX * BS / 4);
+            const int rr = tile_r * BS + r, cc = tile_c * BS + 4 * w;
+            uint32_t v = 0;
+            if (rr < a.H) {
+                const uint8_t *p = prev_plane + (size_t)rr * a.pitch;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (cc + k < a.W) v |= (uint32_t)p[cc + k] << (8 * k);
+            }
+            *reinterpret_cast<uint32_t *>(anchors + r * APITCH + 4 * w) = v;
+        }
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);   // tells the compiler it is warp-uniform
@@ -469,13 +502,13 @@ __global__ void __launch_bounds__(NT) bbme_diamond16_kernel(const __grid_constan
     const int fr_lo = max(2, wr0 + 2), fr_hi = min(rmax - 2, wr0 + a.win_h - 18);
     const int fc_lo = max(2, wc0 + 2), fc_hi = min(cmax - 2, wc0 + 2 + a.win_w - 36);
     const int Rl = min(lane, 19);                              // neighbourhood row this lane loads
-    const bool prev_vec = ((reinterpret_cast<uintptr_t>(a.prev) | a.pitch | a.prev_stride) & 15) == 0;
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
 
-    for (int b = warp; b < a.tbx * a.tby; b += NT / 32) {
-        const int bi = tile_r + b / a.tbx, bj = tile_c + b % a.tbx;
+    for (int b = warp; b < TBX * TBY; b += NT / 32) {
+        const int bi = tile_r + b / TBX, bj = tile_c + b % TBX;
         if (bi >= a.R || bj >= a.C) continue;
         const int br = bi * BS, bc = bj * BS;
+        const uint8_t *anchor0 = anchors + (b / TBX) * BS * APITCH + (b % TBX) * BS;   // top-left pixel of the anchor block
 
         // anchor rows for the register path: anc[d] = anchor row lane - d, scored when a candidate has dr = d - 2;
         // msk[d] zeroes the contribution of lanes whose row lies outside that candidate
@@ -484,16 +517,8 @@ __global__ void __launch_bounds__(NT) bbme_diamond16_kernel(const __grid_constan
         for (int d = 0; d < 5; d++) {
             const int k = lane - d;
             const bool ok = lane < 20 && k >= 0 && k < BS;
-            const uint8_t *p = prev_plane + (size_t)(br + (ok ? k : 0)) * a.pitch + bc;
-            if (prev_vec) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-                anc[d][0] = v.x; anc[d][1] = v.y; anc[d][2] = v.z; anc[d][3] = v.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    anc[d][i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
-                                ((uint32_t)p[4 * i + 3] << 24);
-            }
+            const uint4 v = *reinterpret_cast<const uint4 *>(anchor0 + clampi(k, 0, BS - 1) * APITCH);
+            anc[d][0] = v.x; anc[d][1] = v.y; anc[d][2] = v.z; anc[d][3] = v.w;
             msk[d] = ok ? 0xFFFFFFFFu : 0u;
         }
 
@@ -778,20 +803,23 @@ template <int PNORM>
 static int launch_diamond16(PatternArgs a, int n, cudaStream_t stream)
 {
     constexpr int NT = 256, BS = 16;
-    const int tbx = min(8, a.C), tby = min(4, a.R);
+    const int tbx = 8, tby = 4;                          // fixed in the kernel (TBX, TBY)
     const int margin = 32;
     int win_w = tbx * BS + 2 * margin + 4 + 15;          // as launch_fast: funnel slack + 16-byte rounding of column 0
     win_w = (win_w + 15) / 16 * 16;
     const int win_h = tby * BS + 2 * margin;
     a.tbx = tbx; a.tby = tby; a.margin = margin; a.win_w = win_w; a.win_h = win_h;
     CUtensorMap map;
-    a.use_tma = make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h) ? 1 : 0;
-    if (!a.use_tma) memset(&map, 0, sizeof(map));
-    const size_t smem = (size_t)win_w * win_h + 64;      // slack: the register path reads 36 bytes from a 16-byte boundary
+    CUtensorMap pmap;
+    a.use_tma = (make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h) &&
+                 make_plane_tensor_map(&pmap, a.prev, n, a.H, a.W, a.pitch, a.prev_stride, 144, tby * BS)) ? 1 : 0;
+    if (!a.use_tma) { memset(&map, 0, sizeof(map)); memset(&pmap, 0, sizeof(pmap)); }
+    // window (+64: the register path reads 36 bytes from a 16-byte boundary), then the anchor tile (144 x 64)
+    const size_t smem = (((size_t)win_w * win_h + 64 + 127) & ~(size_t)127) + (size_t)144 * tby * BS;
     auto kern = bbme_diamond16_kernel<PNORM, NT>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
-    kern<<<grid, NT, smem, stream>>>(map, a);
+    kern<<<grid, NT, smem, stream>>>(map, pmap, a);
     note_launch();
     return check_launch("bbme_diamond16_kernel");
 }
