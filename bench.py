@@ -246,7 +246,16 @@ def bench_exhaustive(D, N, torch, planes, dev):
     return out
 
 
+def emit(obj, real_stdout):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL banners ...) was sent to stderr."""
+    os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    # keep stdout clean for the single JSON line: fd 1 is pointed at stderr while the bench runs
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -287,13 +296,13 @@ def main():
             t += dt
         value = per_step * args.steps / t
         sample = f"{per_step} pairs per step drawn cyclically from an {nf}-frame sequence, one pair per thread"
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64",
             "data": "synthetic", "config": config,
             "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, real_stdout)
         return
 
     # ------------------------------------------------------------------ the B200 arm
@@ -463,7 +472,7 @@ def main():
         "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "bbme_exhaustive": exhaustive,
         "cpu_baseline": cpu, "parity": parity,
     }
-    print(json.dumps(out))
+    emit(out, real_stdout)
     if world > 1:
         dist.destroy_process_group()
 

@@ -336,3 +336,85 @@ def test_pipeline_properties_4k(D):
     same = D.Pipeline(1, H, W)
     same.run(pp, pp)
     assert same.psnr()[0] == -1 or same.psnr()[0].real > 40      # static content: the -1 edge vectors cost little
+
+
+# ------------------------------------------------------------------ sequence mode, host runner, stage timing
+def test_sequence_aliasing_equals_separate_buffers(D):
+    """gme_pipeline builds each frame's pyramid once when prev/cur are two views of one sequence buffer; the
+    results must equal the run on two unrelated buffers (pyramids built per pair, as the reference does)."""
+    seq = S.zoom_rotate_sequence(7, 272, 400, zoom_per_frame=0.004, deg_per_frame=0.3, seed=31)
+    d, n = 2, 5
+    planes = D.Planes.from_host(seq)
+    a = D.Pipeline(n, 272, 400)
+    a.run(planes.view(0, n), planes.view(d, d + n))
+    prev, cur = D.Planes.from_host(seq[:n].copy()), D.Planes.from_host(seq[d:d + n].copy())
+    b = D.Pipeline(n, 272, 400)
+    b.run(prev, cur)
+    torch.cuda.synchronize()
+    assert torch.equal(a.params, b.params) and torch.equal(a.sse, b.sse)
+    assert torch.equal(a.comp.pixels(), b.comp.pixels())
+    for which in range(6):
+        assert torch.equal(a.intermediate(which), b.intermediate(which)), which
+    want = O.global_motion_estimation(seq[1], seq[1 + d])
+    np.testing.assert_allclose(a.params[1].cpu().numpy(), want, **PARAM_TOL)
+
+
+def test_host_sequence_runner_matches_pipeline(D):
+    """The overlapped host path (chunked uploads on a copy stream, two alternating device buffers) returns the
+    rows the resident pipeline computes, call after call, including a ragged last chunk."""
+    seq = S.pan_sequence(14, 160, 208, step=(2, 1), seed=9)
+    d = 3
+    n = seq.shape[0] - d
+    planes = D.Planes.from_host(seq)
+    pipe = D.Pipeline(n, 160, 208)
+    pipe.run(planes.view(0, n), planes.view(d, d + n))
+    runner = D.HostSequenceRunner(seq.shape[0], 160, 208, d, chunk=4)
+    host = torch.from_numpy(seq).pin_memory()
+    for _ in range(3):                                   # alternates the two device buffers
+        rows = runner.run(host)
+        torch.cuda.synchronize()
+        got = rows.numpy()
+        np.testing.assert_array_equal(got[:, :6], pipe.params.cpu().numpy())
+        np.testing.assert_array_equal(got[:, 6].astype(np.int64), pipe.sse.cpu().numpy())
+        assert (got[:, 7] == 0).all()
+    assert runner.h2d_bytes == seq.size and runner.d2h_bytes == n * 8 * 8
+
+
+def test_stage_timing_api(D):
+    import gme_native as N
+    seq = S.pan_sequence(6, 96, 160, seed=2)
+    planes = D.Planes.from_host(seq)
+    pipe = D.Pipeline(4, 96, 160)
+    N.stage_timing_enable(True)
+    for _ in range(3):
+        pipe.run(planes.view(0, 4), planes.view(2, 6))
+    ms, calls = N.stage_timing_read()
+    N.stage_timing_enable(False)
+    assert calls == 3 and len(ms) == N.PIPELINE_STAGES and all(m > 0 for m in ms)
+    pipe.run(planes.view(0, 4), planes.view(2, 6))
+    assert N.stage_timing_read()[1] == 0                 # disabled: nothing recorded
+
+
+@pytest.mark.parametrize("H,W", [(17, 17), (18, 40), (33, 33), (48, 400), (130, 150), (64, 1000)])
+def test_diamond16_small_and_border_frames(D, H, W):
+    """The register-neighbourhood diamond kernel: frames barely larger than a block (every centre is clamped),
+    frames narrower than a tile, and the H % 16 == 0 last-row quirk -- all against the oracle, both norms."""
+    rng = np.random.default_rng(H * 1000 + W)
+    base = S.texture(H + 12, W + 12, seed=H + W)
+    prev = np.ascontiguousarray(base[6:6 + H, 6:6 + W])
+    dy, dx = (int(v) for v in rng.integers(-5, 6, 2))
+    cur = np.ascontiguousarray(base[6 - dy:6 - dy + H, 6 - dx:6 - dx + W])
+    for pn in (0, 1):
+        want = O.get_motion_field(prev, cur, 16, 0, 3, pn)
+        np.testing.assert_array_equal(field_of(D, prev, cur, 16, 0, 3, pn)[0], want)
+    np.testing.assert_array_equal(field_of(D, prev, prev, 16, 0, 3, 1)[0], O.get_motion_field(prev, prev, 16, 0, 3, 1))
+
+
+def test_sad_probe_counts(D):
+    import ctypes
+    import gme_native as N
+    scratch = torch.zeros(1024, dtype=torch.int32, device="cuda")
+    n = ctypes.c_uint64(0)
+    N.check(N.lib.gme_sad_peak_probe(1, 148, 16, scratch.data_ptr(), ctypes.byref(n), None))
+    torch.cuda.synchronize()
+    assert n.value == 148 * 256 * 16 * 4 * 8 * 4
