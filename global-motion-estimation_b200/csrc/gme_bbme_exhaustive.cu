@@ -13,6 +13,10 @@
 // Tie-breaking: the reference scans column offset outer, row offset inner and keeps the first
 // strict minimum (bbme.py:146-174).  A thread sees its row offsets in ascending order (strict
 // '<'), threads are merged by a 64-bit key (cost, column index, row index) with atomicMin.
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
 #include "gme_common.cuh"
 
 namespace gme {
@@ -167,6 +171,231 @@ __global__ void __launch_bounds__(NT) bbme_exhaustive_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------
+// Second-generation tiled kernel (block sizes 8, 12, 16).  What changed against the kernel above, and why
+// (ncu, profiles/r01e_*): the 16 x 16 x 4 fully unrolled update did not fit the instruction cache
+// (no_instruction was the top stall), 116-130 registers allowed one CTA per SM, every window row cost
+// BS-1 wasted fill/drain rows, and the funnel shifts and min-updates competed with VABSDIFF4 for the ALU pipe.
+//   * TWO threads share a column offset: thread h scores anchor rows h*BS/2 .. and walks window rows
+//     BS/2*h lower, so both finish candidate j in the same iteration and one SHFL adds the halves.
+//     Half the accumulators and anchor registers (2-3 CTAs per SM), a quarter of the unrolled code,
+//     and only BS/2-1 fill rows.
+//   * the window is expanded once per CTA into four byte-shifted copies, so the inner loop loads
+//     aligned words and never shifts.  The copies use a row pitch = 2 (mod 4) words and a copy stride
+//     = 4 (mod 32) words: 16 consecutive byte columns x 2 halves hit 32 different banks.
+//   * the running first-minimum is one VIMNMX on the key (cost << 8 | row index).
+//   * rows that can only belong to out-of-frame candidates are not visited at all.
+// ---------------------------------------------------------------------------------------
+struct Exhaustive2Geom {
+    int tpb;          // column offsets handled per macroblock per pass (thread pairs)
+    int rawpw;        // raw window pitch, words
+    int cpitch;       // shifted-copy row pitch, words (= 2 mod 4)
+    int cstride;      // words between the four copies (= 4 mod 32)
+};
+
+template <int BS, int PNORM, int SPLIT>
+__global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_constant__ CUtensorMap cur_map,
+                                                                  ExhaustiveArgs a, Exhaustive2Geom g)
+{
+    static_assert(BS % 4 == 0 && BS >= 8 && (SPLIT == 1 || SPLIT == 2), "block sizes 8, 12, 16");
+    constexpr int WPR = BS / 4, HB = BS / SPLIT;     // HB anchor rows per thread
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+
+    const int NT = blockDim.x;
+    const int plane = blockIdx.z, bi = blockIdx.y, bj0 = blockIdx.x * a.nb;
+    const int br = bi * BS, bc0 = bj0 * BS;
+    const int ncand = 2 * a.sw + BS;
+    const int wr0 = br - a.sw, wc0 = (bc0 - a.sw) & ~15;         // TMA: 16-byte aligned first column
+    const int xoff = (bc0 - a.sw) - wc0;
+    const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
+    const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
+
+    uint32_t *raw = reinterpret_cast<uint32_t *>(smem);
+    const size_t raw_bytes = ((size_t)a.win_w * a.win_h + 127) / 128 * 128;
+    uint32_t *copies = reinterpret_cast<uint32_t *>(smem + raw_bytes);                               // [4][cstride]
+    uint32_t *anchors = copies + 4 * g.cstride;                                                      // [nb][BS][WPR]
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(anchors + a.nb * BS * WPR + (a.nb * BS * WPR & 1));
+
+    // ---- stage: raw window (TMA), anchor blocks, result keys ----------------------------------------------
+    if (a.use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&bar, (uint32_t)(a.win_w * a.win_h));
+            tma_load_3d(smem, &cur_map, &bar, wc0, wr0, plane);
+        }
+    } else {
+        for (int i = threadIdx.x; i < g.rawpw * a.win_h; i += NT) {
+            const int rr = wr0 + i / g.rawpw, cc = wc0 + (i % g.rawpw) * 4;
+            uint32_t v = 0;
+            if (rr >= 0 && rr < a.H) {
+                const uint8_t *p = cur_plane + (size_t)rr * a.pitch;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (cc + k >= 0 && cc + k < a.W) v |= (uint32_t)p[cc + k] << (8 * k);
+            }
+            raw[i] = v;
+        }
+    }
+    for (int i = threadIdx.x; i < a.nb * BS * WPR; i += NT) {
+        const int b = i / (BS * WPR), r = (i / WPR) % BS, w = i % WPR;
+        uint32_t v = 0;
+        if (bj0 + b < a.C) {
+            const uint8_t *p = prev_plane + (size_t)(br + r) * a.pitch + (bc0 + b * BS) + 4 * w;
+            v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        }
+        anchors[i] = v;
+    }
+    for (int i = threadIdx.x; i < a.nb; i += NT) keys[i] = ~0ull;
+    __syncthreads();
+    if (a.use_tma) mbar_wait(&bar, 0);
+
+    // ---- four byte-shifted copies of the window ----------------------------------------------------------------
+    for (int i = threadIdx.x; i < a.win_h * g.cpitch; i += NT) {
+        const int r = i / g.cpitch, w = i - r * g.cpitch;
+        const uint32_t lo = w < g.rawpw ? raw[r * g.rawpw + w] : 0u;
+        const uint32_t hi = w + 1 < g.rawpw ? raw[r * g.rawpw + w + 1] : 0u;
+        copies[i] = lo;
+        copies[g.cstride + i] = __funnelshift_r(lo, hi, 8);
+        copies[2 * g.cstride + i] = __funnelshift_r(lo, hi, 16);
+        copies[3 * g.cstride + i] = __funnelshift_r(lo, hi, 24);
+    }
+    __syncthreads();
+
+    // ---- search ---------------------------------------------------------------------------------------------
+    const int q = threadIdx.x / SPLIT, h = threadIdx.x % SPLIT;
+    const int b = q / g.tpb, t_in = q - b * g.tpb;
+    const bool block_ok = b < a.nb && bj0 + b < a.C;
+    const int bb = block_ok ? b : 0;
+    uint32_t anc[HB][WPR];
+#pragma unroll
+    for (int k = 0; k < HB; k++)
+#pragma unroll
+        for (int w = 0; w < WPR; w++) anc[k][w] = anchors[(bb * BS + h * HB + k) * WPR + w];
+
+    // row offsets j (wr = j - sw) whose candidate is inside the frame: 0 <= br + wr <= H - BS  (bbme.py:157-162)
+    const int jlo = max(0, a.sw - br), jhi = min(ncand - 1, a.H - BS - br + a.sw);
+    const int nj = jhi - jlo + 1, nrows = nj + HB - 1;
+    const int bc = bc0 + bb * BS;
+    unsigned long long best_key = ~0ull;
+    for (int pass = 0; pass * g.tpb < ncand; pass++) {
+        const int ci = t_in + pass * g.tpb;
+        const int left = bc + ci - a.sw;
+        const bool active = block_ok && ci < ncand && left >= 0 && left <= a.W - BS && nj > 0;   // column part of bbme.py:157-162
+        // both threads of a pair share `active`, so the pair either walks the window or skips it together
+        const unsigned pair_mask = SPLIT == 2 ? __ballot_sync(0xFFFFFFFFu, active) : 0u;
+        if (!active) continue;
+        const int x0 = xoff + bb * BS + ci;                                             // byte column inside the window
+        const uint32_t *row = copies + (x0 & 3) * g.cstride + (jlo + h * HB) * g.cpitch + (x0 >> 2);
+        uint32_t acc[HB];
+#pragma unroll
+        for (int s = 0; s < HB; s++) acc[s] = 0;
+        uint32_t key = 0xFFFFFFFFu;
+        // one window row: it is row h*HB + k of candidate t - k for every k it can still belong to
+        auto step = [&](auto tt_c, auto first_c, int t0) {
+            constexpr int tt = decltype(tt_c)::value;
+            constexpr bool first = decltype(first_c)::value;
+            uint32_t w[WPR];
+#pragma unroll
+            for (int i = 0; i < WPR; i++) w[i] = row[i];
+            row += g.cpitch;
+#pragma unroll
+            for (int k = 0; k < HB; k++) {
+                if (first && k > tt) continue;               // fill: candidate tt - k < 0 does not exist
+                const int s = (tt - k + HB) % HB;
+#pragma unroll
+                for (int i = 0; i < WPR; i++) acc[s] = cost4_acc<PNORM>(w[i], anc[k][i], acc[s]);
+            }
+            if (!first || tt == HB - 1) {                    // candidate t - HB + 1 is complete in both halves
+                constexpr int sdone = (tt + 1) % HB;
+                uint32_t total = acc[sdone];
+                if (SPLIT == 2) total += __shfl_xor_sync(pair_mask, total, 1);
+                acc[sdone] = 0;
+                key = min(key, total * 256u + (uint32_t)(t0 + tt - (HB - 1)));   // first minimum: smaller row index wins ties
+            }
+        };
+#define GME_STEP(tt, first) step(std::integral_constant<int, tt>{}, std::integral_constant<bool, first>{}, t0)
+#define GME_ROWS(first, guard)                                                                                      \
+        do {                                                                                                        \
+            if (!(guard) || t0 + 0 < nrows) GME_STEP(0, first);                                                     \
+            if (HB > 1 && (!(guard) || t0 + 1 < nrows)) GME_STEP((1 % HB), first);                                  \
+            if (HB > 2 && (!(guard) || t0 + 2 < nrows)) GME_STEP((2 % HB), first);                                  \
+            if (HB > 3 && (!(guard) || t0 + 3 < nrows)) GME_STEP((3 % HB), first);                                  \
+            if (HB > 4 && (!(guard) || t0 + 4 < nrows)) GME_STEP((4 % HB), first);                                  \
+            if (HB > 5 && (!(guard) || t0 + 5 < nrows)) GME_STEP((5 % HB), first);                                  \
+            if (HB > 6 && (!(guard) || t0 + 6 < nrows)) GME_STEP((6 % HB), first);                                  \
+            if (HB > 7 && (!(guard) || t0 + 7 < nrows)) GME_STEP((7 % HB), first);                                  \
+            if (HB > 8 && (!(guard) || t0 + 8 < nrows)) GME_STEP((8 % HB), first);                                  \
+            if (HB > 9 && (!(guard) || t0 + 9 < nrows)) GME_STEP((9 % HB), first);                                  \
+            if (HB > 10 && (!(guard) || t0 + 10 < nrows)) GME_STEP((10 % HB), first);                               \
+            if (HB > 11 && (!(guard) || t0 + 11 < nrows)) GME_STEP((11 % HB), first);                               \
+        } while (0)
+        int t0 = 0;
+        // nrows = nj + HB - 1 >= HB: the first block of HB rows always exists in full and is the (triangular) fill
+        GME_ROWS(true, false);
+        for (t0 = HB; t0 + HB <= nrows; t0 += HB) GME_ROWS(false, false);
+        if (t0 < nrows) GME_ROWS(false, true);
+#undef GME_ROWS
+#undef GME_STEP
+        if (h == 0 && key != 0xFFFFFFFFu) {
+            const unsigned long long k64 = ((unsigned long long)(key >> 8) << 32) | ((unsigned long long)ci << 16) |
+                                           (unsigned long long)(jlo + (int)(key & 255u));
+            best_key = k64 < best_key ? k64 : best_key;
+        }
+    }
+    if (best_key != ~0ull) atomicMin(&keys[bb], best_key);
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.nb; i += NT) {
+        if (bj0 + i < a.C) {
+            const unsigned long long key = keys[i];
+            const int ci = (int)((key >> 16) & 0xFFFF), j = (int)(key & 0xFFFF);
+            int32_t *f = a.field + (((size_t)plane * a.R + bi) * a.C + bj0 + i) * 2;
+            f[0] = ci - a.sw;      // column offset -> channel 0 (bbme.py:176)
+            f[1] = j - a.sw;       // row offset    -> channel 1 (bbme.py:177)
+        }
+    }
+}
+
+template <int BS, int PNORM>
+static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *handled)
+{
+    // two threads per column offset pay off when a thread's share of the anchor would not fit the registers /
+    // the unrolled update would not fit the instruction cache (block size 16); smaller blocks keep one thread
+    constexpr int WPR = BS / 4, SPLIT = BS >= 16 ? 2 : 1;
+    const int ncand = 2 * a.sw + BS;
+    *handled = false;
+    if (ncand > 256 || getenv("GME_EXH_OLD")) return GME_OK;     // key packs the row index in 8 bits
+    Exhaustive2Geom g;
+    g.tpb = min(ncand, 384 / SPLIT);
+    const int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
+    const int threads = (nb * g.tpb * SPLIT + 31) / 32 * 32;
+    const int win_h = 2 * a.sw + 2 * BS - 1;
+    int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4 + 15;  // +15: the first column is rounded down to 16 bytes
+    win_w = (win_w + 15) / 16 * 16;
+    g.rawpw = win_w / 4;
+    g.cpitch = g.rawpw + 2;                                      // rawpw = 0 (mod 4)  ->  2 (mod 4)
+    g.cstride = (win_h * g.cpitch + 31) / 32 * 32 + (SPLIT == 2 ? 4 : 8);   // 4 (mod 32); one thread per column: 8
+    const size_t raw_bytes = ((size_t)win_w * win_h + 127) / 128 * 128;
+    const size_t smem = raw_bytes + (size_t)4 * g.cstride * 4 + (size_t)(nb * BS * WPR + 1) * 4 + (size_t)nb * 8 + 16;
+    if (smem > 100 * 1024) return GME_OK;                        // window too large: previous kernel / generic path
+    a.nb = nb; a.tpb = g.tpb; a.win_w = win_w; a.win_h = win_h;
+    CUtensorMap map;
+    a.use_tma = (win_w <= 256 && win_h <= 256 &&
+                 make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h)) ? 1 : 0;
+    if (!a.use_tma) memset(&map, 0, sizeof(map));
+    auto kern = bbme_exhaustive2_kernel<BS, PNORM, SPLIT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((a.C + nb - 1) / nb, a.R, n);
+    kern<<<grid, threads, smem, stream>>>(map, a, g);
+    note_launch();
+    *handled = true;
+    return check_launch("bbme_exhaustive2_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
 // Generic path: any block size / window, a warp per macroblock, lanes over candidates.
 // ---------------------------------------------------------------------------------------
 template <int PNORM>
@@ -250,9 +479,15 @@ static int launch_exhaustive_pn(ExhaustiveArgs a, int n, int bs, cudaStream_t st
     switch (bs) {
     case 2: rc = launch_fast<2, PNORM>(a, n, stream, &handled); break;
     case 4: rc = launch_fast<4, PNORM>(a, n, stream, &handled); break;
-    case 8: rc = launch_fast<8, PNORM>(a, n, stream, &handled); break;
-    case 12: rc = launch_fast<12, PNORM>(a, n, stream, &handled); break;
-    case 16: rc = launch_fast<16, PNORM>(a, n, stream, &handled); break;
+    case 8: rc = launch_fast2<8, PNORM>(a, n, stream, &handled);
+            if (!handled && rc == GME_OK) rc = launch_fast<8, PNORM>(a, n, stream, &handled);
+            break;
+    case 12: rc = launch_fast2<12, PNORM>(a, n, stream, &handled);
+             if (!handled && rc == GME_OK) rc = launch_fast<12, PNORM>(a, n, stream, &handled);
+             break;
+    case 16: rc = launch_fast2<16, PNORM>(a, n, stream, &handled);
+             if (!handled && rc == GME_OK) rc = launch_fast<16, PNORM>(a, n, stream, &handled);
+             break;
     default: break;
     }
     if (handled || rc != GME_OK) return rc;
