@@ -53,91 +53,112 @@ __device__ __forceinline__ void block_sum_u32_to_u64(unsigned int v, unsigned lo
     }
 }
 
-// 16 pixels of one row per thread; block (32, 8): a warp covers 512 consecutive pixels of a row.
+// A thread owns 16 consecutive pixels of kCompRows consecutive rows (all inside one macroblock row when the block
+// size is a multiple of kCompRows, so they share one motion vector): the loads of the rows are independent, which
+// gives the memory system four requests per thread to overlap.  Block (32, 8): a CTA covers 512 x 32 pixels.
+constexpr int kCompRows = 4;
+
 template <bool HAS_CUR>
 __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
 {
     const int plane = blockIdx.z;
-    const int a_row = blockIdx.y * 8 + threadIdx.y;
+    const int row0 = (blockIdx.y * 8 + threadIdx.y) * kCompRows;
     const int b0 = (blockIdx.x * 32 + threadIdx.x) * 16;
     unsigned int err = 0;
-    if (a_row < a.H && b0 < a.W) {
+    if (row0 < a.H && b0 < a.W) {
         const uint8_t *fplane = a.frame + (size_t)plane * a.fstride;
-        const uint8_t *frow = fplane + (size_t)a_row * a.fp;
-        uint8_t *orow = a.comp + (size_t)plane * a.ostride + (size_t)a_row * a.op;
-        const uint8_t *crow = HAS_CUR ? a.cur + (size_t)plane * a.cstride + (size_t)a_row * a.cp : nullptr;
+        const uint8_t *cplane = HAS_CUR ? a.cur + (size_t)plane * a.cstride : nullptr;
+        uint8_t *oplane = a.comp + (size_t)plane * a.ostride;
         const int npx = min(16, a.W - b0);
-        const int i = a_row / a.bs, j0 = b0 / a.bs;
-        const bool fast = a.vec_ok && npx == 16 && j0 == (b0 + 15) / a.bs;
+        const int j0 = b0 / a.bs;
+        const bool fast = a.vec_ok && npx == 16 && j0 == (b0 + 15) / a.bs && a.bs % kCompRows == 0;
         if (fast) {
-            // branch-light gather of the 16-pixel run: aligned 32-bit loads of the source run (words that lie
-            // outside the row are not touched), funnel shift to the destination alignment, then -- only for runs
-            // that straddle the frame edge -- a per-byte blend with the unmoved pixels (motion.py:311-318)
-            uint32_t px[4];
-            int lo = 16, hi = 0;                                             // bytes [lo, hi) of the run are moved
-            int na = 0, s0 = 0;
+            // branch-light gather of 16-pixel runs: aligned 32-bit loads of the source run (words that lie outside
+            // the row are not touched), funnel shift to the destination alignment, then -- only for runs that
+            // straddle the frame edge -- a per-byte blend with the unmoved pixels (motion.py:311-318)
+            const int i = row0 / a.bs;
+            int lo = 16, hi = 0, d1 = 0, s0 = 0;                             // bytes [lo, hi) of a run are moved
             if (i < a.R && j0 < a.C) {
-                int d0, d1;
+                int d0;
                 load_vector(a, plane, i, j0, d0, d1);
                 d0 = clampi(d0, -(1 << 24), 1 << 24);                        // any |d| >= frame size: source outside
                 d1 = clampi(d1, -(1 << 24), 1 << 24);
-                na = a_row - d1;                                             // motion.py:312-313
-                s0 = b0 - d0;
-                if (na >= 0 && na < a.H) {
-                    lo = max(0, -s0);
-                    hi = min(16, a.W - s0);
+                s0 = b0 - d0;                                                // motion.py:313
+                lo = max(0, -s0);
+                hi = min(16, a.W - s0);
+            }
+            const int sa = s0 & ~3;                                          // floor to a word boundary (also for s0 < 0)
+            const int sh = (s0 - sa) * 8;
+            const bool inside = sa >= 0 && sa + 20 <= (int)a.fp;
+            uint32_t px[kCompRows][4];
+            uint4 cur4[kCompRows];
+            bool moved[kCompRows];
+#pragma unroll
+            for (int r = 0; r < kCompRows; r++) {
+                const int a_row = row0 + r;
+                const int na = a_row - d1;                                   // motion.py:312
+                moved[r] = lo < hi && a_row < a.H && na >= 0 && na < a.H;
+                if (a_row < a.H) {
+                    if (moved[r]) {
+                        const uint8_t *srow = fplane + (size_t)na * a.fp;
+                        uint32_t w[5];
+                        if (inside) {
+#pragma unroll
+                            for (int k = 0; k < 5; k++) w[k] = __ldg(reinterpret_cast<const uint32_t *>(srow + sa) + k);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 5; k++) {
+                                const int c = sa + 4 * k;
+                                w[k] = (c >= 0 && c + 4 <= (int)a.fp) ? __ldg(reinterpret_cast<const uint32_t *>(srow + c)) : 0u;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++) px[r][k] = __funnelshift_r(w[k], w[k + 1], sh);
+                    }
+                    if (!moved[r] || lo > 0 || hi < 16) {                    // some pixels stay where they are
+                        const uint4 v = *reinterpret_cast<const uint4 *>(fplane + (size_t)a_row * a.fp + b0);
+                        const uint32_t orig[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t m = moved[r] ? (byte_mask(clampi(hi - 4 * k, 0, 4)) & ~byte_mask(clampi(lo - 4 * k, 0, 4))) : 0u;
+                            px[r][k] = (moved[r] ? (px[r][k] & m) : 0u) | (orig[k] & ~m);
+                        }
+                    }
+                    if (HAS_CUR) cur4[r] = *reinterpret_cast<const uint4 *>(cplane + (size_t)a_row * a.cp + b0);
                 }
             }
-            if (lo < hi) {
-                const int sa = s0 & ~3;                                      // floor to a word boundary (also for s0 < 0)
-                const int sh = (s0 - sa) * 8;
-                const uint8_t *srow = fplane + (size_t)na * a.fp;
-                uint32_t r[5];
-                if (sa >= 0 && sa + 20 <= (int)a.fp) {
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>(srow + sa);
 #pragma unroll
-                    for (int k = 0; k < 5; k++) r[k] = __ldg(w + k);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 5; k++) {
-                        const int c = sa + 4 * k;
-                        r[k] = (c >= 0 && c + 4 <= (int)a.fp) ? __ldg(reinterpret_cast<const uint32_t *>(srow + c)) : 0u;
+            for (int r = 0; r < kCompRows; r++) {
+                const int a_row = row0 + r;
+                if (a_row < a.H) {
+                    *reinterpret_cast<uint4 *>(oplane + (size_t)a_row * a.op + b0) = make_uint4(px[r][0], px[r][1], px[r][2], px[r][3]);
+                    if (HAS_CUR) {
+                        err = ssd4_acc(px[r][0], cur4[r].x, err);
+                        err = ssd4_acc(px[r][1], cur4[r].y, err);
+                        err = ssd4_acc(px[r][2], cur4[r].z, err);
+                        err = ssd4_acc(px[r][3], cur4[r].w, err);
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < 4; k++) px[k] = __funnelshift_r(r[k], r[k + 1], sh);
-            }
-            if (lo > 0 || hi < 16) {                                         // some pixels stay where they are
-                const uint4 v = *reinterpret_cast<const uint4 *>(frow + b0);
-                const uint32_t orig[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t m = (lo < hi) ? (byte_mask(clampi(hi - 4 * k, 0, 4)) & ~byte_mask(clampi(lo - 4 * k, 0, 4))) : 0u;
-                    px[k] = (lo < hi ? (px[k] & m) : 0u) | (orig[k] & ~m);
-                }
-            }
-            *reinterpret_cast<uint4 *>(orow + b0) = make_uint4(px[0], px[1], px[2], px[3]);
-            if (HAS_CUR) {
-                const uint4 c = *reinterpret_cast<const uint4 *>(crow + b0);
-                err = ssd4_acc(px[0], c.x, err);
-                err = ssd4_acc(px[1], c.y, err);
-                err = ssd4_acc(px[2], c.z, err);
-                err = ssd4_acc(px[3], c.w, err);
             }
         } else {
-            for (int k = 0; k < npx; k++) {
-                const int b = b0 + k, j = b / a.bs;
-                uint8_t v = frow[b];
-                if (i < a.R && j < a.C) {
-                    int d0, d1;
-                    load_vector(a, plane, i, j, d0, d1);
-                    const long na = (long)a_row - d1, nb = (long)b - d0;
-                    if (na >= 0 && na < a.H && nb >= 0 && nb < a.W) v = fplane[(size_t)na * a.fp + nb];
-                }
-                orow[b] = v;
-                if (HAS_CUR) {
-                    const int d = (int)v - (int)crow[b];
-                    err += (unsigned int)(d * d);
+            for (int a_row = row0; a_row < min(row0 + kCompRows, a.H); a_row++) {
+                const uint8_t *frow = fplane + (size_t)a_row * a.fp;
+                uint8_t *orow = oplane + (size_t)a_row * a.op;
+                const int i = a_row / a.bs;
+                for (int k = 0; k < npx; k++) {
+                    const int b = b0 + k, j = b / a.bs;
+                    uint8_t v = frow[b];
+                    if (i < a.R && j < a.C) {
+                        int d0, d1;
+                        load_vector(a, plane, i, j, d0, d1);
+                        const long na = (long)a_row - d1, nb = (long)b - d0;
+                        if (na >= 0 && na < a.H && nb >= 0 && nb < a.W) v = fplane[(size_t)na * a.fp + nb];
+                    }
+                    orow[b] = v;
+                    if (HAS_CUR) {
+                        const int d = (int)v - (int)cplane[(size_t)a_row * a.cp + b];
+                        err += (unsigned int)(d * d);
+                    }
                 }
             }
         }
@@ -192,7 +213,7 @@ int launch_compensate(const uint8_t *frame, size_t fp, size_t fstride, const voi
     a.vec_ok = (aligned16(frame, fp, fstride) && aligned16(comp, op, ostride) && (!cur || aligned16(cur, cp, cstride))) ? 1 : 0;
     a.sse = reinterpret_cast<unsigned long long *>(sse);
     dim3 block(32, 8);
-    dim3 grid(((W + 15) / 16 + block.x - 1) / block.x, (H + block.y - 1) / block.y, n);
+    dim3 grid(((W + 15) / 16 + block.x - 1) / block.x, (H + block.y * kCompRows - 1) / (block.y * kCompRows), n);
     if (cur && sse) {
         cudaMemsetAsync(sse, 0, sizeof(uint64_t) * n, stream);
         compensate_kernel<true><<<grid, block, 0, stream>>>(a);
