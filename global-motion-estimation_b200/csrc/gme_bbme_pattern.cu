@@ -712,6 +712,164 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------
+// Diamond search on 2 x 2 blocks -- the dense first estimate of the GME pipeline (motion.py:27-29).
+//
+// One THREAD per block (the walks of neighbouring blocks diverge, so nothing is shared between
+// lanes).  The nine LDSP candidates lie in the 6 x 6 pixel neighbourhood of the centre: the thread
+// loads it once per step (6 rows x 3 aligned words, byte-aligned with two funnel shifts per row),
+// then each candidate's four pixels are gathered with ONE byte permute from two row registers and
+// scored with VABSDIFF4 (+ IDP.4A) against the anchor word.  The first minimum comes from a
+// min over (cost << 4 | index) keys.  The SDSP reuses the registers of the last LDSP step.  Steps
+// whose neighbourhood leaves the staged window or on which the clamp of bbme.py:503-504 could act
+// use the candidate-at-a-time evaluator (BlockEval<2, 1>).  The per-plane channel sums that the
+// first estimate needs are accumulated here (see PatternArgs::sums).
+// ---------------------------------------------------------------------------------------
+template <int PNORM, int NT>
+__global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
+{
+    constexpr int BS = 2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+
+    const int plane = blockIdx.z;
+    const int tile_r = blockIdx.y * a.tby, tile_c = blockIdx.x * a.tbx;
+    const int wr0 = tile_r * BS - a.margin, wc0 = (tile_c * BS - a.margin) & ~15;
+    const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
+    const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
+
+    stage_window(smem, &bar, &cur_map, a.use_tma, cur_plane, plane, a.H, a.W, a.pitch, wr0, wc0, a.win_w, a.win_h);
+
+    BlockEval<BS, 1, PNORM> e;                        // fallback evaluator
+    e.cur_plane = cur_plane;
+    e.win = reinterpret_cast<const uint32_t *>(smem);
+    e.pitch = a.pitch;
+    e.win_pw = a.win_w / 4;
+    e.wr0 = wr0;
+    e.wc0 = wc0;
+    e.wr1 = wr0 + a.win_h;
+    e.wc1 = wc0 + a.win_w - 4;
+    e.lane_g = 0;
+    e.gmask = 1u << (threadIdx.x & 31);
+
+    constexpr int LR[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};      // LDSP offsets (row, col), bbme.py:463-472
+    constexpr int LC[9] = {0, 0, 1, 2, 1, 0, -1, -2, -1};
+    constexpr int SR[5] = {0, 0, 1, 0, -1};                    // SDSP as applied (swapped), bbme.py:474-480,518-521
+    constexpr int SC[5] = {0, 1, 0, -1, 0};
+    constexpr unsigned long long LRP = 0x321012342ull, LCP = 0x101234322ull;   // the same tables as nibbles (value + 2)
+    constexpr unsigned SRP = 0x12322u, SCP = 0x21232u;
+    const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
+    // centres for which the register path applies: no clamp can act, and rows mr-2 .. mr+3 / the three aligned
+    // words that hold columns mc-2 .. mc+3 lie inside the staged window
+    const int fr_lo = max(2, wr0 + 2), fr_hi = min(rmax - 2, wr0 + a.win_h - 4);
+    const int fc_lo = max(2, wc0 + 2), fc_hi = min(cmax - 2, wc0 + 2 + a.win_w - 12);
+    const uint32_t *win = reinterpret_cast<const uint32_t *>(smem);
+    const int win_pw = a.win_w / 4;
+
+    int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
+    int sum0 = 0, sum1 = 0;
+    for (int b = threadIdx.x; b < a.tbx * a.tby; b += NT) {
+        const int bi = tile_r + b / a.tbx, bj = tile_c + b % a.tbx;
+        if (bi >= a.R || bj >= a.C) continue;
+        const int br = bi * BS, bc = bj * BS;
+        e.load_anchor(prev_plane, br, bc);                       // anchor[0] = row 0 (2 bytes), anchor[1] = row 1
+        const uint32_t anchor = (e.anchor[0] & 0xFFFFu) | (e.anchor[1] << 16);
+
+        uint32_t z0[6], z1[6];                                   // row i: z0 = bytes 0..3, z1 = bytes 4..7 (byte 0 = column mc - 2)
+        auto cost_of = [&](uint32_t px) -> uint32_t { return cost4_acc<PNORM>(px, anchor, 0u); };
+        int mr = br, mc = bc;
+        bool last_fast = false;
+        uint32_t centre_cost = 0;
+        for (;;) {                                               // LDSP, bbme.py:494-513
+            if (mr >= fr_lo && mr <= fr_hi && mc >= fc_lo && mc <= fc_hi) {
+                const int x = mc - 2 - wc0;
+                const uint32_t *p = win + (mr - 2 - wr0) * win_pw + (x >> 2);
+                const int sh = (x & 3) * 8;
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const uint32_t w0 = p[i * win_pw], w1 = p[i * win_pw + 1], w2 = p[i * win_pw + 2];
+                    z0[i] = __funnelshift_r(w0, w1, sh);
+                    z1[i] = __funnelshift_r(w1, w2, sh);
+                }
+                // candidate (dr, dc): rows dr+2, dr+3; bytes dc+2, dc+3 of each
+                uint32_t c[9];
+                c[0] = cost_of(__byte_perm(z0[2], z0[3], 0x7632));                                            // ( 0,  0)
+                c[1] = cost_of(__byte_perm(z0[4], z0[5], 0x7632));                                            // ( 2,  0)
+                c[2] = cost_of(__byte_perm(__funnelshift_r(z0[3], z1[3], 24), __funnelshift_r(z0[4], z1[4], 24), 0x5410));   // ( 1,  1)
+                c[3] = cost_of(__byte_perm(z1[2], z1[3], 0x5410));                                            // ( 0,  2)
+                c[4] = cost_of(__byte_perm(__funnelshift_r(z0[1], z1[1], 24), __funnelshift_r(z0[2], z1[2], 24), 0x5410));   // (-1,  1)
+                c[5] = cost_of(__byte_perm(z0[0], z0[1], 0x7632));                                            // (-2,  0)
+                c[6] = cost_of(__byte_perm(z0[1], z0[2], 0x6521));                                            // (-1, -1)
+                c[7] = cost_of(__byte_perm(z0[2], z0[3], 0x5410));                                            // ( 0, -2)
+                c[8] = cost_of(__byte_perm(z0[3], z0[4], 0x6521));                                            // ( 1, -1)
+                uint32_t key = c[0] << 4;                        // first strict minimum in candidate order; costs < 2^18
+#pragma unroll
+                for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
+                const int kb = (int)(key & 15u);
+                if (kb == 0) { last_fast = true; centre_cost = c[0]; break; }
+                mr += (int)((LRP >> (4 * kb)) & 15) - 2;
+                mc += (int)((LCP >> (4 * kb)) & 15) - 2;
+            } else {
+                int r[9], cc[9];
+                uint32_t cost[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    r[k] = clampi(mr + LR[k], 0, rmax);
+                    cc[k] = clampi(mc + LC[k], 0, cmax);
+                }
+                e.template eval<9>(r, cc, cost);
+                uint32_t best = kInfCost;
+                int best_r = mr, best_c = mc;
+#pragma unroll
+                for (int k = 0; k < 9; k++)
+                    if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = cc[k]; }
+                if (best_r == mr && best_c == mc) { last_fast = false; break; }
+                mr = best_r;
+                mc = best_c;
+            }
+        }
+        int out_r, out_c;
+        if (last_fast) {                                         // SDSP on the registers of the last step
+            uint32_t key = centre_cost << 4;
+            key = min(key, (cost_of(__byte_perm(__funnelshift_r(z0[2], z1[2], 24), __funnelshift_r(z0[3], z1[3], 24), 0x5410)) << 4) | 1u);   // (0, +1)
+            key = min(key, (cost_of(__byte_perm(z0[3], z0[4], 0x7632)) << 4) | 2u);                           // (+1, 0)
+            key = min(key, (cost_of(__byte_perm(z0[2], z0[3], 0x6521)) << 4) | 3u);                           // (0, -1)
+            key = min(key, (cost_of(__byte_perm(z0[1], z0[2], 0x7632)) << 4) | 4u);                           // (-1, 0)
+            const int ks = (int)(key & 15u);
+            out_r = mr + (int)((SRP >> (4 * ks)) & 15) - 2;
+            out_c = mc + (int)((SCP >> (4 * ks)) & 15) - 2;
+        } else {
+            int r[5], cc[5];
+            uint32_t cost[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                r[k] = clampi(mr + SR[k], 0, rmax);
+                cc[k] = clampi(mc + SC[k], 0, cmax);
+            }
+            e.template eval<5>(r, cc, cost);
+            uint32_t best = kInfCost;
+            out_r = mr;
+            out_c = mc;
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (cost[k] < best) { best = cost[k]; out_r = r[k]; out_c = cc[k]; }
+        }
+        const int o0 = out_c - bc, o1 = out_r - br;              // bbme.py:531-532
+        *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(o0, o1);
+        sum0 += o0;
+        sum1 += o1;
+    }
+    if (a.sums) {
+        __syncwarp();
+        sum0 = __reduce_add_sync(0xFFFFFFFFu, sum0);
+        sum1 = __reduce_add_sync(0xFFFFFFFFu, sum1);
+        if ((threadIdx.x & 31) == 0) {
+            if (sum0) atomicAdd(a.sums + 2 * plane, (unsigned long long)(long long)sum0);
+            if (sum1) atomicAdd(a.sums + 2 * plane + 1, (unsigned long long)(long long)sum1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Generic path: any block size 1..255, a full warp per macroblock, global memory only.
 // ---------------------------------------------------------------------------------------
 template <int PNORM>
@@ -828,8 +986,32 @@ static int launch_diamond16(PatternArgs a, int n, cudaStream_t stream)
 }
 
 template <int PNORM>
+static int launch_diamond2(PatternArgs a, int n, cudaStream_t stream)
+{
+    constexpr int NT = 256, BS = 2;
+    const int tbx = min(32, a.C), tby = min(16, a.R);
+    const int margin = 12;
+    int win_w = tbx * BS + 2 * margin + 4 + 15;
+    win_w = (win_w + 15) / 16 * 16;
+    if (win_w % 32 == 0) win_w += 16;
+    const int win_h = tby * BS + 2 * margin;
+    a.tbx = tbx; a.tby = tby; a.margin = margin; a.win_w = win_w; a.win_h = win_h;
+    CUtensorMap map;
+    a.use_tma = make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h) ? 1 : 0;
+    if (!a.use_tma) memset(&map, 0, sizeof(map));
+    const size_t smem = (size_t)win_w * win_h + 32;
+    auto kern = bbme_diamond2_kernel<PNORM, NT>;
+    dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
+    kern<<<grid, NT, smem, stream>>>(map, a);
+    note_launch();
+    return check_launch("bbme_diamond2_kernel");
+}
+
+template <int PNORM>
 static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
 {
+    if (bs == 2 && a.procedure == GME_SEARCH_DIAMOND && getenv("GME_DIAMOND2_OLD") == nullptr)
+        return launch_diamond2<PNORM>(a, n, stream);
     if (bs == 16 && a.procedure == GME_SEARCH_DIAMOND && !a.sums && getenv("GME_DIAMOND16_OLD") == nullptr)
         return launch_diamond16<PNORM>(a, n, stream);
     switch (bs) {
