@@ -498,10 +498,11 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
     constexpr unsigned SRP = 0x12322u, SCP = 0x21232u;
     const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
     // centres for which the register path applies: no clamp can act on the 5 x 5 neighbourhood of offsets, and the
-    // 20 x 20 pixel neighbourhood (read as 36 bytes from a 16-byte boundary) lies inside the staged window
+    // 20 x 20 pixel neighbourhood (read as 6 aligned words) lies inside the staged window
     const int fr_lo = max(2, wr0 + 2), fr_hi = min(rmax - 2, wr0 + a.win_h - 18);
-    const int fc_lo = max(2, wc0 + 2), fc_hi = min(cmax - 2, wc0 + 2 + a.win_w - 36);
+    const int fc_lo = max(2, wc0 + 2), fc_hi = min(cmax - 2, wc0 + 2 + a.win_w - 24);
     const int Rl = min(lane, 19);                              // neighbourhood row this lane loads
+    const uint32_t row_base = smem_u32(smem) + (uint32_t)(Rl * a.win_w);
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
 
     for (int b = warp; b < TBX * TBY; b += NT / 32) {
@@ -519,24 +520,19 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
             const bool ok = lane < 20 && k >= 0 && k < BS;
             const uint4 v = *reinterpret_cast<const uint4 *>(anchor0 + clampi(k, 0, BS - 1) * APITCH);
             anc[d][0] = v.x; anc[d][1] = v.y; anc[d][2] = v.z; anc[d][3] = v.w;
-            msk[d] = ok ? 0xFFFFFFFFu : 0u;
+            msk[d] = ok ? 1u : 0u;
         }
 
         uint32_t z[5] = {0, 0, 0, 0, 0};   // bytes 0..19 of this lane's neighbourhood row; byte 0 = image column mc - 2
         auto load_region = [&](int mr, int mc) {
+            // six aligned words that cover bytes xs .. xs+19 of this lane's row, read at a run-time word address
+            // (32-bit shared address kept in a register: no generic-address arithmetic in the loop)
             const int xs = mc - 2 - wc0;
-            const int o = xs & 15;
-            const uint8_t *p = smem + (mr - 2 - wr0 + Rl) * a.win_w + (xs & ~15);
-            const uint4 q0 = *reinterpret_cast<const uint4 *>(p), q1 = *reinterpret_cast<const uint4 *>(p + 16);
-            const uint32_t v8 = *reinterpret_cast<const uint32_t *>(p + 32);
+            const uint32_t addr = row_base + (uint32_t)((mr - 2 - wr0) * a.win_w + (xs & ~3));
             uint32_t u[6];
-            switch (o >> 2) {              // warp-uniform
-            case 0: u[0] = q0.x; u[1] = q0.y; u[2] = q0.z; u[3] = q0.w; u[4] = q1.x; u[5] = q1.y; break;
-            case 1: u[0] = q0.y; u[1] = q0.z; u[2] = q0.w; u[3] = q1.x; u[4] = q1.y; u[5] = q1.z; break;
-            case 2: u[0] = q0.z; u[1] = q0.w; u[2] = q1.x; u[3] = q1.y; u[4] = q1.z; u[5] = q1.w; break;
-            default: u[0] = q0.w; u[1] = q1.x; u[2] = q1.y; u[3] = q1.z; u[4] = q1.w; u[5] = v8; break;
-            }
-            const int bsh = (o & 3) * 8;
+#pragma unroll
+            for (int i = 0; i < 6; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u[i]) : "r"(addr + 4 * i));
+            const int bsh = (xs & 3) * 8;
 #pragma unroll
             for (int i = 0; i < 5; i++) z[i] = __funnelshift_r(u[i], u[i + 1], bsh);
         };
@@ -545,7 +541,7 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
             uint32_t acc = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) acc = cost4_acc<PNORM>(s[i], anc[d][i], acc);
-            return __reduce_add_sync(0xFFFFFFFFu, acc & msk[d]);
+            return __reduce_add_sync(0xFFFFFFFFu, acc * msk[d]);     // msk: 0 / 1 (IMAD: the FMA pipe has room, the ALU pipe does not)
         };
         auto shifted = [&](int bits, uint32_t (&s)[4]) {
 #pragma unroll
