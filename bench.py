@@ -264,6 +264,7 @@ def main():
     ap.add_argument("--workload", default="gme_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="upload/compute chunks per step of the host-frames arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -335,7 +336,7 @@ def main():
         dev_out[:, 7] = pipe.status.to(torch.float64)
         return dev_out
 
-    runner = D.HostSequenceRunner(nf, H, W, DISTANCE, chunk=max(1, pairs // 4), procedure=procedure, window=window,
+    runner = D.HostSequenceRunner(nf, H, W, DISTANCE, chunk=max(1, -(-pairs // max(1, args.e2e_chunks))), procedure=procedure, window=window,
                                   device=dev)
 
     def step(e2e: bool):
