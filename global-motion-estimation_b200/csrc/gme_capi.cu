@@ -22,6 +22,8 @@ int launch_first_params(const int32_t *, int, int, int, double *, cudaStream_t);
 int launch_affine_fit(const int32_t *, int, int, int, int, int, double, int, int, double *, uint8_t *, int32_t *,
                       int16_t *, int32_t *, int, const long long *, long, cudaStream_t);
 int launch_affine_field(const double *, int, int, int, int16_t *, cudaStream_t);
+int launch_pipeline_fits(const int32_t *, int, int, int, int, uint8_t *, const int32_t *, int, int, int, int, uint8_t *,
+                         int, double, double *, int32_t *, const long long *, long, int16_t *, cudaStream_t);
 int launch_compensate(const uint8_t *, size_t, size_t, const void *, int, int, int, const uint8_t *, size_t, size_t,
                       uint8_t *, size_t, size_t, int, int, int, uint64_t *, cudaStream_t);
 int launch_sse(const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t, int, int, int, uint64_t *,
@@ -265,6 +267,7 @@ int gme_affine_fit(const int32_t *gt_field, int n, int R, int C, int level_h, in
 {
     if (!gt_field || !params || n < 0 || level_h <= 0 || level_w <= 0) return GME_ERR_INVALID_ARGUMENT;
     if (R <= 0 || C <= 0) return GME_ERR_UNSUPPORTED;   // empty field: the reference indexes an empty array
+    if ((long long)R * C > 0x7FFFFFFFLL) return GME_ERR_UNSUPPORTED;
     if (n == 0) return GME_OK;
     return launch_affine_fit(gt_field, n, R, C, level_h, level_w, pct, robust, project, params, outlier, threshold,
                              model_field, status, 0, nullptr, 0, static_cast<cudaStream_t>(stream));
@@ -380,14 +383,13 @@ int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *c
     timer.mark();
     if (status && cudaMemsetAsync(status, 0, sizeof(int32_t) * n, st) != cudaSuccess) return check_launch("memset");
     // the sequential part: first estimate, then project + robust fit per level (motion.py:128-134)
-    // (the first estimate -- the mean of the dense field -- is formed inside the level-1 fit from the channel sums)
-    GME_TRY(launch_affine_fit(f1, n, L.R1, L.C1, L.l1.H, L.l1.W, 0.3, 1, 1, params, out1, nullptr, nullptr, status, 1,
-                              reinterpret_cast<const long long *>(sums), (long)L.R0 * L.C0, st));
-    GME_TRY(launch_affine_fit(f2, n, L.R2, L.C2, H, W, 0.3, 1, 1, params, out2, nullptr, nullptr, status, 1, nullptr, 0, st));
+    // one launch: first estimate (mean of the dense field, from the channel sums) -> project + robust fit on L1 ->
+    // project + robust fit on L2 -> model field of the final parameters at block_size 16 (results.py:52-54)
+    GME_TRY(launch_pipeline_fits(f1, L.R1, L.C1, L.l1.H, L.l1.W, out1, f2, L.R2, L.C2, H, W, out2, n, 0.3, params, status,
+                                 reinterpret_cast<const long long *>(sums), (long)L.R0 * L.C0, comp ? model : nullptr, st));
     timer.mark();
     if (comp) {
-        // results.py:52-59,109: model field at block_size 16, compensate previous, PSNR against current
-        GME_TRY(launch_affine_field(params, n, L.R2, L.C2, model, st));
+        // motion.compensate_frame of previous + the squared error against current (results.py:59,109)
         GME_TRY(launch_compensate(prev, pitch, prev_plane_stride, model, 1, L.R2, L.C2, sse ? cur : nullptr, pitch,
                                   cur_plane_stride, comp, comp_pitch, comp_plane_stride, n, H, W, sse, st));
     }

@@ -79,21 +79,27 @@ __global__ void affine_field_kernel(const double *params, int R, int C, int16_t 
     *reinterpret_cast<short2 *>(field + ((size_t)blockIdx.y * N + idx) * 2) = make_short2((short)m0, (short)m1);
 }
 
-struct FitArgs {
-    const int32_t *gt;
+struct FitLevel {
+    const int32_t *gt;       // BBME field of this level, int32[n][R][C][2]
     int R, C;
-    double w;        // 1 / (level_h * level_w)   (motion.py:250)
-    double pct;      // MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE
-    int robust, project;
-    double *params;
-    uint8_t *outlier;
+    double w;                // 1 / (level_h * level_w)   (motion.py:250)
+    uint8_t *outlier;        // optional outputs of this level
     int32_t *threshold;
     int16_t *model_field;
+};
+
+struct FitArgs {
+    FitLevel lv[2];          // the pipeline fits L1 and L2 in ONE launch (the second starts from the first's result)
+    int nlevels;
+    double pct;              // MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE
+    int robust, project;
+    double *params;
     int32_t *status;
-    int status_or;   // OR into status instead of overwriting (pipeline: a singular level must stay flagged)
+    int status_or;           // OR into status instead of overwriting
     const long long *first_sums;   // pipeline: per-pair channel sums of the dense field (written by the dense
     long first_count;              // BBME kernel); the first estimate (motion.py:186-188) is formed here
-    int cache_diffs;               // the N distances fit in dynamic shared memory
+    size_t cache_bytes;            // dynamic shared memory available for the distances of one level
+    int16_t *final_field;          // optional: model field of the FINAL parameters on the last level's grid
 };
 
 // 3x3 inverse the way np.linalg.inv gets it (dgesv on the identity): LU with partial pivoting,
@@ -145,7 +151,7 @@ constexpr int kRadixBits = 11, kRadixBins = 1 << kRadixBits;
 
 __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
 {
-    extern __shared__ __align__(16) unsigned int diff_cache[];   // [N] when a.cache_diffs
+    extern __shared__ __align__(16) unsigned int diff_cache[];   // [N] of the current level when it fits
     __shared__ long long red[kFitWarps][12];
     __shared__ unsigned int hist[kRadixBins];
     __shared__ unsigned int warp_tot[kFitWarps];
@@ -153,163 +159,199 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
     __shared__ unsigned int sel_prefix, sel_rank, sh_dmax;
 
     const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long N = (long)a.R * a.C;
-    const int32_t *gt = a.gt + (size_t)pair * N * 2;
     double *params = a.params + (size_t)pair * 6;
 
     if (tid < 6) {
-        double v;
-        if (a.first_sums) {
-            // motion.compute_first_parameters (motion.py:186-188): float64 mean, stored as float32
-            v = (tid == 0 || tid == 3)
-                    ? (double)(float)((double)a.first_sums[2 * pair + (tid == 3)] / (double)a.first_count) : 0.0;
-        } else {
-            v = params[tid];
-        }
-        if (a.project && (tid == 0 || tid == 3)) v = v * 2.0;    // motion.parameter_projection (motion.py:204-207)
-        p[tid] = v;
+        if (a.first_sums)   // motion.compute_first_parameters (motion.py:186-188): float64 mean, stored as float32
+            p[tid] = (tid == 0 || tid == 3)
+                         ? (double)(float)((double)a.first_sums[2 * pair + (tid == 3)] / (double)a.first_count) : 0.0;
+        else
+            p[tid] = params[tid];
     }
-    if (tid == 0) sh_dmax = 0;
-    __syncthreads();
+    int st_all = 0;
 
-    // ---- L1 distance between the BBME field and the model field (motion.py:232-239) --------
-    auto diff_at = [&](long idx) -> unsigned int {
-        int m0, m1;
-        model_vector(p, (int)(idx / a.C), (int)(idx % a.C), m0, m1);
-        const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * idx);
-        return (unsigned int)(abs(g.x - m0) + abs(g.y - m1));
-    };
-    auto diff_of = [&](long idx) -> unsigned int { return a.cache_diffs ? diff_cache[idx] : diff_at(idx); };
-
-    unsigned int thr = 0xFFFFFFFFu;
-    if (a.robust) {
-        // threshold = sorted(diff)[N - int(pct*N)]  (element 0 when int(pct*N) == 0: Python's [-0])
-        const long t = (long)(a.pct * (double)N);
-        unsigned int rank = (unsigned int)(t == 0 ? 0 : N - t);   // 0-based rank of the threshold
-        unsigned int prefix = 0;                                   // bits of the answer found so far
-        unsigned int dmax = 0;
-        for (long i = tid; i < N; i += kFitBig) {
-            int m0, m1;
-            model_vector(p, (int)(i / a.C), (int)(i % a.C), m0, m1);
-            const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * i);
-            const unsigned int d = (unsigned int)(abs(g.x - m0) + abs(g.y - m1));
-            if (a.cache_diffs) diff_cache[i] = d;
-            dmax = max(dmax, d);
-            if (a.model_field)
-                *reinterpret_cast<short2 *>(a.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
-        }
-        dmax = __reduce_max_sync(0xFFFFFFFFu, dmax);
-        if (lane == 0 && dmax) atomicMax(&sh_dmax, dmax);
+    for (int level = 0; level < a.nlevels; level++) {
+        const FitLevel L = a.lv[level];
+        const int N = L.R * L.C;
+        const int32_t *gt = L.gt + (size_t)pair * N * 2;
+        const bool cached = a.robust && (size_t)N * sizeof(unsigned int) <= a.cache_bytes;
         __syncthreads();
-        dmax = sh_dmax;
-        // exact radix select, 11 bits per pass, starting at the highest digit that is populated
-        int shift = 0;
-        while (shift + kRadixBits < 32 && (dmax >> (shift + kRadixBits)) != 0) shift += kRadixBits;
-        for (; shift >= 0; shift -= kRadixBits) {
-            for (int i = tid; i < kRadixBins; i += kFitBig) hist[i] = 0;
-            __syncthreads();
-            const unsigned int hi_mask = (shift + kRadixBits >= 32) ? 0u : (0xFFFFFFFFu << (shift + kRadixBits));
-            for (long i = tid; i < N; i += kFitBig) {
-                const unsigned int d = diff_of(i);
-                if ((d & hi_mask) == prefix) atomicAdd(&hist[(d >> shift) & (kRadixBins - 1)], 1u);
-            }
-            __syncthreads();
-            // each thread owns 2 consecutive bins; block-wide exclusive scan of the pair sums by warp shuffles
-            const unsigned int b0 = hist[2 * tid], b1 = hist[2 * tid + 1];
-            unsigned int incl = b0 + b1;
+        if (a.project && (tid == 0 || tid == 3)) p[tid] = p[tid] * 2.0;   // motion.parameter_projection (motion.py:204-207)
+        if (tid == 0) sh_dmax = 0;
+        __syncthreads();
+
+        // ---- L1 distance between the BBME field and the model field (motion.py:232-239) --------
+        auto diff_at = [&](int idx) -> unsigned int {
+            int m0, m1;
+            model_vector(p, idx / L.C, idx % L.C, m0, m1);
+            const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * idx);
+            return (unsigned int)(abs(g.x - m0) + abs(g.y - m1));
+        };
+        auto diff_of = [&](int idx) -> unsigned int { return cached ? diff_cache[idx] : diff_at(idx); };
+
+        unsigned int thr = 0xFFFFFFFFu;
+        if (a.robust) {
+            // threshold = sorted(diff)[N - int(pct*N)]  (element 0 when int(pct*N) == 0: Python's [-0])
+            const int t = (int)(a.pct * (double)N);
+            unsigned int rank = (unsigned int)(t == 0 ? 0 : N - t);   // 0-based rank of the threshold
+            unsigned int prefix = 0;                                   // bits of the answer found so far
+            unsigned int dmax = 0;
+            // the field is read with four independent loads in flight per thread: the kernel is latency-bound
+            for (int base = tid; base < N; base += 4 * kFitBig) {
+                int2 g[4];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += up;
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * kFitBig;
+                    g[u] = i < N ? __ldg(reinterpret_cast<const int2 *>(gt + 2 * i)) : make_int2(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * kFitBig;
+                    if (i < N) {
+                        int m0, m1;
+                        model_vector(p, i / L.C, i % L.C, m0, m1);
+                        const unsigned int d = (unsigned int)(abs(g[u].x - m0) + abs(g[u].y - m1));
+                        if (cached) diff_cache[i] = d;
+                        dmax = max(dmax, d);
+                        if (L.model_field)
+                            *reinterpret_cast<short2 *>(L.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
+                    }
+                }
             }
-            if (lane == 31) warp_tot[warp] = incl;
+            dmax = __reduce_max_sync(0xFFFFFFFFu, dmax);
+            if (lane == 0 && dmax) atomicMax(&sh_dmax, dmax);
             __syncthreads();
-            if (warp == 0) {
-                unsigned int v = warp_tot[lane], sc = v;
+            dmax = sh_dmax;
+            // exact radix select, 11 bits per pass, starting at the highest digit that is populated
+            int shift = 0;
+            while (shift + kRadixBits < 32 && (dmax >> (shift + kRadixBits)) != 0) shift += kRadixBits;
+            for (; shift >= 0; shift -= kRadixBits) {
+                for (int i = tid; i < kRadixBins; i += kFitBig) hist[i] = 0;
+                __syncthreads();
+                const unsigned int hi_mask = (shift + kRadixBits >= 32) ? 0u : (0xFFFFFFFFu << (shift + kRadixBits));
+                for (int i = tid; i < N; i += kFitBig) {
+                    const unsigned int d = diff_of(i);
+                    if ((d & hi_mask) == prefix) atomicAdd(&hist[(d >> shift) & (kRadixBins - 1)], 1u);
+                }
+                __syncthreads();
+                // each thread owns 2 consecutive bins; block-wide exclusive scan of the pair sums by warp shuffles
+                const unsigned int b0 = hist[2 * tid], b1 = hist[2 * tid + 1];
+                unsigned int incl = b0 + b1;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int up = __shfl_up_sync(0xFFFFFFFFu, sc, o);
-                    if (lane >= o) sc += up;
+                    const unsigned int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += up;
                 }
-                warp_tot[lane] = sc - v;                           // exclusive
+                if (lane == 31) warp_tot[warp] = incl;
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned int v = warp_tot[lane], sc = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int up = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+                        if (lane >= o) sc += up;
+                    }
+                    warp_tot[lane] = sc - v;                           // exclusive
+                }
+                __syncthreads();
+                const unsigned int before = warp_tot[warp] + incl - (b0 + b1);
+                if (rank >= before && rank < before + b0 + b1) {       // exactly one thread
+                    const bool second = rank >= before + b0;
+                    sel_prefix = prefix | ((unsigned int)(2 * tid + (second ? 1 : 0)) << shift);
+                    sel_rank = rank - before - (second ? b0 : 0u);
+                }
+                __syncthreads();
+                prefix = sel_prefix;
+                rank = sel_rank;
+                __syncthreads();
             }
-            __syncthreads();
-            const unsigned int before = warp_tot[warp] + incl - (b0 + b1);
-            if (rank >= before && rank < before + b0 + b1) {       // exactly one thread
-                const bool second = rank >= before + b0;
-                sel_prefix = prefix | ((unsigned int)(2 * tid + (second ? 1 : 0)) << shift);
-                sel_rank = rank - before - (second ? b0 : 0u);
+            thr = prefix;
+        } else if (L.model_field) {
+            for (int i = tid; i < N; i += kFitBig) {
+                int m0, m1;
+                model_vector(p, i / L.C, i % L.C, m0, m1);
+                *reinterpret_cast<short2 *>(L.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
             }
-            __syncthreads();
-            prefix = sel_prefix;
-            rank = sel_rank;
-            __syncthreads();
         }
-        thr = prefix;
-    } else if (a.model_field) {
-        for (long i = tid; i < N; i += kFitBig) {
-            int m0, m1;
-            model_vector(p, (int)(i / a.C), (int)(i % a.C), m0, m1);
-            *reinterpret_cast<short2 *>(a.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
-        }
-    }
 
-    // ---- masked normal equations (motion.py:246-282): twelve exact integer sums -----------
-    long long S[12];
+        // ---- masked normal equations (motion.py:246-282): twelve exact integer sums -----------
+        long long S[12];
 #pragma unroll
-    for (int k = 0; k < 12; k++) S[k] = 0;
-    for (long i = tid; i < N; i += kFitBig) {
-        const bool out = a.robust ? (diff_of(i) > thr) : false;   // strict '>' (motion.py:244)
-        if (a.outlier) a.outlier[(size_t)pair * N + i] = out ? 1 : 0;
-        if (!out) {
-            const long long x = 4 * (i / a.C), y = 4 * (i % a.C);  // motion.py:254-255
-            const int2 g = *reinterpret_cast<const int2 *>(gt + 2 * i);
-            S[0] += 1;      S[1] += x;          S[2] += y;
-            S[3] += x * x;  S[4] += x * y;      S[5] += y * y;
-            S[6] += g.x;    S[7] += x * g.x;    S[8] += y * g.x;
-            S[9] += g.y;    S[10] += x * g.y;   S[11] += y * g.y;
+        for (int k = 0; k < 12; k++) S[k] = 0;
+        for (int base = tid; base < N; base += 4 * kFitBig) {
+            int2 g[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * kFitBig;
+                g[u] = i < N ? __ldg(reinterpret_cast<const int2 *>(gt + 2 * i)) : make_int2(0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * kFitBig;
+                if (i < N) {
+                    const bool out = a.robust ? (diff_of(i) > thr) : false;   // strict '>' (motion.py:244)
+                    if (L.outlier) L.outlier[(size_t)pair * N + i] = out ? 1 : 0;
+                    if (!out) {
+                        const long long x = 4 * (i / L.C), y = 4 * (i % L.C);  // motion.py:254-255 (32-bit division)
+                        S[0] += 1;         S[1] += x;             S[2] += y;
+                        S[3] += x * x;     S[4] += x * y;         S[5] += y * y;
+                        S[6] += g[u].x;    S[7] += x * g[u].x;    S[8] += y * g[u].x;
+                        S[9] += g[u].y;    S[10] += x * g[u].y;   S[11] += y * g[u].y;
+                    }
+                }
+            }
         }
-    }
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) S[k] += __shfl_xor_sync(0xFFFFFFFFu, S[k], o);
-        if (lane == 0) red[warp][k] = S[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < 12; k++) {
-            long long v = red[lane][k];
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-            S[k] = v;
+            for (int o = 16; o >= 1; o >>= 1) S[k] += __shfl_xor_sync(0xFFFFFFFFu, S[k], o);
+            if (lane == 0) red[warp][k] = S[k];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                long long v = red[lane][k];
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                S[k] = v;
+            }
+        }
+
+        if (tid == 0) {
+            const double w = L.w;
+            double M[3][3], inv[3][3];
+            M[0][0] = (double)S[0] * w; M[0][1] = (double)S[1] * w; M[0][2] = (double)S[2] * w;
+            M[1][0] = M[0][1];          M[1][1] = (double)S[3] * w; M[1][2] = (double)S[4] * w;
+            M[2][0] = M[0][2];          M[2][1] = M[1][2];          M[2][2] = (double)S[5] * w;
+            const double r0[3] = {(double)S[6] * w, (double)S[7] * w, (double)S[8] * w};
+            const double r1[3] = {(double)S[9] * w, (double)S[10] * w, (double)S[11] * w};
+            if (inverse3(M, inv)) {
+                for (int r = 0; r < 3; r++) {
+                    p[r] = __dadd_rn(__dadd_rn(__dmul_rn(inv[r][0], r0[0]), __dmul_rn(inv[r][1], r0[1])),
+                                     __dmul_rn(inv[r][2], r0[2]));
+                    p[3 + r] = __dadd_rn(__dadd_rn(__dmul_rn(inv[r][0], r1[0]), __dmul_rn(inv[r][1], r1[1])),
+                                         __dmul_rn(inv[r][2], r1[2]));
+                }
+            } else {
+                st_all |= 1;
+                const double qnan = __longlong_as_double(0x7FF8000000000000LL);
+                for (int r = 0; r < 6; r++) p[r] = qnan;
+            }
+            if (L.threshold) L.threshold[pair] = a.robust ? (int32_t)thr : 0;
         }
     }
-
-    if (tid == 0) {
-        const double w = a.w;
-        double M[3][3], inv[3][3];
-        M[0][0] = (double)S[0] * w; M[0][1] = (double)S[1] * w; M[0][2] = (double)S[2] * w;
-        M[1][0] = M[0][1];          M[1][1] = (double)S[3] * w; M[1][2] = (double)S[4] * w;
-        M[2][0] = M[0][2];          M[2][1] = M[1][2];          M[2][2] = (double)S[5] * w;
-        const double r0[3] = {(double)S[6] * w, (double)S[7] * w, (double)S[8] * w};
-        const double r1[3] = {(double)S[9] * w, (double)S[10] * w, (double)S[11] * w};
-        int st = 0;
-        if (inverse3(M, inv)) {
-            for (int r = 0; r < 3; r++) {
-                params[r] = __dadd_rn(__dadd_rn(__dmul_rn(inv[r][0], r0[0]), __dmul_rn(inv[r][1], r0[1])),
-                                      __dmul_rn(inv[r][2], r0[2]));
-                params[3 + r] = __dadd_rn(__dadd_rn(__dmul_rn(inv[r][0], r1[0]), __dmul_rn(inv[r][1], r1[1])),
-                                          __dmul_rn(inv[r][2], r1[2]));
-            }
-        } else {
-            st = 1;
-            const double qnan = __longlong_as_double(0x7FF8000000000000LL);
-            for (int r = 0; r < 6; r++) params[r] = qnan;
+    __syncthreads();
+    if (tid < 6) params[tid] = p[tid];
+    if (tid == 0 && a.status) a.status[pair] = a.status_or ? (a.status[pair] | st_all) : st_all;
+    if (a.final_field) {                       // motion.get_motion_field_affine with the final parameters (results.py:52-54)
+        const FitLevel L = a.lv[a.nlevels - 1];
+        const int N = L.R * L.C;
+        for (int i = tid; i < N; i += kFitBig) {
+            int m0, m1;
+            model_vector(p, i / L.C, i % L.C, m0, m1);
+            *reinterpret_cast<short2 *>(a.final_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
         }
-        if (a.status) a.status[pair] = a.status_or ? (a.status[pair] | st) : st;
-        if (a.threshold) a.threshold[pair] = a.robust ? (int32_t)thr : 0;
     }
 }
 
@@ -320,28 +362,51 @@ int launch_first_params(const int32_t *dense, int n, int R, int C, double *param
     return check_launch("first_params_kernel");
 }
 
-int launch_affine_fit(const int32_t *gt, int n, int R, int C, int level_h, int level_w, double pct, int robust,
-                      int project, double *params, uint8_t *outlier, int32_t *threshold, int16_t *model_field,
-                      int32_t *status, int status_or, const long long *first_sums, long first_count,
-                      cudaStream_t stream)
+static int launch_fit(FitArgs &a, int n, cudaStream_t stream)
 {
-    FitArgs a;
-    a.gt = gt; a.R = R; a.C = C;
-    a.w = 1.0 / (double)((long long)level_h * level_w);
-    a.pct = pct; a.robust = robust; a.project = project;
-    a.params = params; a.outlier = outlier; a.threshold = threshold; a.model_field = model_field; a.status = status; a.status_or = status_or;
-    a.first_sums = first_sums; a.first_count = first_count;
-    const size_t cache_bytes = (size_t)R * C * sizeof(unsigned int);
-    a.cache_diffs = (robust && cache_bytes <= 160 * 1024) ? 1 : 0;
-    const size_t smem = a.cache_diffs ? cache_bytes : 0;
+    size_t want = 0;
+    for (int l = 0; l < a.nlevels; l++) want = max(want, (size_t)a.lv[l].R * a.lv[l].C * sizeof(unsigned int));
+    a.cache_bytes = a.robust ? min(want, (size_t)160 * 1024) : 0;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(affine_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         configured = true;
     }
-    affine_fit_kernel<<<n, kFitBig, smem, stream>>>(a);
+    affine_fit_kernel<<<n, kFitBig, a.cache_bytes, stream>>>(a);
     note_launch();
     return check_launch("affine_fit_kernel");
+}
+
+int launch_affine_fit(const int32_t *gt, int n, int R, int C, int level_h, int level_w, double pct, int robust,
+                      int project, double *params, uint8_t *outlier, int32_t *threshold, int16_t *model_field,
+                      int32_t *status, int status_or, const long long *first_sums, long first_count,
+                      cudaStream_t stream)
+{
+    FitArgs a{};
+    a.lv[0] = FitLevel{gt, R, C, 1.0 / (double)((long long)level_h * level_w), outlier, threshold, model_field};
+    a.nlevels = 1;
+    a.pct = pct; a.robust = robust; a.project = project;
+    a.params = params; a.status = status; a.status_or = status_or;
+    a.first_sums = first_sums; a.first_count = first_count;
+    a.final_field = nullptr;
+    return launch_fit(a, n, stream);
+}
+
+// The pipeline's sequential tail in one launch: first estimate from the dense channel sums, projection + robust fit
+// on L1, projection + robust fit on L2 (motion.py:128-134), then the model field of the result (results.py:52-54).
+int launch_pipeline_fits(const int32_t *f1, int R1, int C1, int h1, int w1, uint8_t *out1, const int32_t *f2, int R2,
+                         int C2, int h2, int w2, uint8_t *out2, int n, double pct, double *params, int32_t *status,
+                         const long long *first_sums, long first_count, int16_t *final_field, cudaStream_t stream)
+{
+    FitArgs a{};
+    a.lv[0] = FitLevel{f1, R1, C1, 1.0 / (double)((long long)h1 * w1), out1, nullptr, nullptr};
+    a.lv[1] = FitLevel{f2, R2, C2, 1.0 / (double)((long long)h2 * w2), out2, nullptr, nullptr};
+    a.nlevels = 2;
+    a.pct = pct; a.robust = 1; a.project = 1;
+    a.params = params; a.status = status; a.status_or = 1;
+    a.first_sums = first_sums; a.first_count = first_count;
+    a.final_field = final_field;
+    return launch_fit(a, n, stream);
 }
 
 int launch_affine_field(const double *params, int n, int R, int C, int16_t *field, cudaStream_t stream)

@@ -133,8 +133,8 @@ GME_API void *gme_pipeline_workspace_ptr(void *workspace, int n, int H, int W, i
 
 /* Per-stage device timing of gme_pipeline for the bench (roofline of the dominant kernel is measured
  * live, inside the timed region).  While enabled, every gme_pipeline call records cudaEvents on its
- * stream around its stages: 0 pyramids (4 launches), 1 dense L0 BBME, 2 L1 BBME, 3 L2 BBME, 4 first
- * estimate + the two fits (3 launches), 5 model field + compensation + squared error (2 launches).
+ * stream around its stages: 0 pyramids (2 launches for a sequence, 4 otherwise), 1 dense L0 BBME, 2 L1 BBME,
+ * 3 L2 BBME, 4 first estimate + both robust fits + model field (1 launch), 5 compensation + squared error.
  * gme_stage_timing_read synchronises on the last recorded event, adds up the elapsed milliseconds per
  * stage over all calls since the last read into ms_sum[GME_PIPELINE_STAGES], stores the number of calls
  * and clears the record.  Not usable while the stream is being captured into a CUDA graph. */
