@@ -93,8 +93,23 @@ __global__ void __launch_bounds__(kPyrThreads) pyr_down_kernel(PyrArgs a)
     if (!generic) {
         const int col = col_t + 16 * lane;
         if (lane <= last_chunk && col >= 0 && col < a.W) {
-            for (int r = warp; r < rows_needed; r += kPyrThreads / 32)
-                cp_async16(tile + r * kPyrInPitch + 16 * lane, splane + (size_t)reflect101(row_t + r, a.H) * a.sp + col);
+            uint32_t dst = smem_u32(tile) + (uint32_t)(warp * kPyrInPitch + 16 * lane);
+            if (row_t >= 0 && row_t + rows_needed <= a.H) {        // no row is reflected: walk two pointers
+                const uint8_t *src = splane + (size_t)(row_t + warp) * a.sp + col;
+                const size_t step = (size_t)(kPyrThreads / 32) * a.sp;
+#pragma unroll 4
+                for (int r = warp; r < rows_needed; r += kPyrThreads / 32) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    dst += (kPyrThreads / 32) * kPyrInPitch;
+                    src += step;
+                }
+            } else {
+                for (int r = warp; r < rows_needed; r += kPyrThreads / 32) {
+                    const uint8_t *src = splane + (size_t)reflect101(row_t + r, a.H) * a.sp + col;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    dst += (kPyrThreads / 32) * kPyrInPitch;
+                }
+            }
         }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
