@@ -418,3 +418,31 @@ def test_sad_probe_counts(D):
     N.check(N.lib.gme_sad_peak_probe(1, 148, 16, scratch.data_ptr(), ctypes.byref(n), None))
     torch.cuda.synchronize()
     assert n.value == 148 * 256 * 16 * 4 * 8 * 4
+
+
+def test_unaligned_pitch_takes_the_cooperative_paths(D):
+    """Planes whose pitch is a multiple of 4 but not of 16 cannot travel by TMA / 128-bit accesses: every kernel
+    then takes its cooperative-load / per-pixel path, and the results must not change."""
+    H, W, n, d = 100, 150, 3, 2
+    seq = S.pan_sequence(n + d, H, W, step=(3, -1), seed=14)
+    odd = torch.zeros((n + d, H, 152), dtype=torch.uint8, device="cuda")           # pitch 152: 8 (mod 16)
+    odd[:, :, :W].copy_(torch.from_numpy(seq))
+    planes = D.Planes(odd, W)
+    assert planes.pitch == 152
+    for bs, sw, sp, pn in ((16, 0, 3, 1), (2, 0, 3, 1), (16, 6, 0, 0), (12, 4, 0, 1), (8, 5, 1, 1), (16, 8, 2, 0)):
+        got = D.motion_field(planes.view(0, n), planes.view(d, d + n), bs, sw, sp, pn).cpu().numpy()
+        for k in range(n):
+            np.testing.assert_array_equal(got[k], O.get_motion_field(seq[k], seq[k + d], bs, sw, sp, pn),
+                                          err_msg=f"bs={bs} sw={sw} sp={sp} pn={pn} pair={k}")
+    np.testing.assert_array_equal(D.pyr_down(planes).to_host()[1], O.pyr_down(seq[1]))
+    pipe = D.Pipeline(n, H, W)
+    comp_odd = D.Planes(torch.zeros((n, H, 152), dtype=torch.uint8, device="cuda"), W)
+    pipe.comp = comp_odd                                                            # unaligned output planes too
+    pipe.run(planes.view(0, n), planes.view(d, d + n))
+    torch.cuda.synchronize()
+    for k in range(n):
+        want = O.global_motion_estimation(seq[k], seq[k + d])
+        np.testing.assert_allclose(pipe.params[k].cpu().numpy(), want, **PARAM_TOL)
+        comp = O.compensate_frame(seq[k], O.get_motion_field_affine((H // 16, W // 16), want))
+        np.testing.assert_array_equal(pipe.comp.to_host()[k], comp)
+        assert int(pipe.sse[k].item()) == O.sse(seq[k + d], comp)
