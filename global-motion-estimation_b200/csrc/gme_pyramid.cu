@@ -19,10 +19,9 @@
 namespace gme {
 
 constexpr int kPyrTileX = 128;                    // output pixels per tile row
-constexpr int kPyrTileY = 64;                     // output rows per tile
 constexpr int kPyrRY = 4;                         // output rows per thread
-constexpr int kPyrThreads = (kPyrTileX / 8) * (kPyrTileY / kPyrRY);   // 256
-constexpr int kPyrInRows = 2 * kPyrTileY + 3;     // 131
+// output rows per tile: 64 (256 threads, 131 input rows) for large levels, 32 (128 threads) for small ones, where
+// the coarser tile grid would waste a quarter of the CTAs on rows past the frame
 constexpr int kPyrInPitch = 2 * kPyrTileX + 32;   // 288 bytes: 16 bytes of left padding, tile, halo, padding
 constexpr int kPyrChunks = kPyrInPitch / 16;      // 18
 
@@ -72,8 +71,11 @@ __device__ __forceinline__ void hrow(const uint8_t *row, int c0, uint32_t (&h)[4
     }
 }
 
-__global__ void __launch_bounds__(kPyrThreads) pyr_down_kernel(PyrArgs a)
+template <int kPyrTileY>
+__global__ void __launch_bounds__((kPyrTileX / 8) * (kPyrTileY / kPyrRY)) pyr_down_kernel(PyrArgs a)
 {
+    constexpr int kPyrThreads = (kPyrTileX / 8) * (kPyrTileY / kPyrRY);
+    constexpr int kPyrInRows = 2 * kPyrTileY + 3;
     extern __shared__ __align__(16) uint8_t tile[];   // [kPyrInRows][kPyrInPitch]
     const int ox_t = blockIdx.x * kPyrTileX, oy_t = blockIdx.y * kPyrTileY;
     const uint8_t *splane = a.src + (size_t)blockIdx.z * a.sstride;
@@ -193,14 +195,15 @@ int launch_pyr_down(const uint8_t *src, size_t sp, size_t sstride, uint8_t *dst,
     a.H = H; a.W = W; a.Ho = (H + 1) / 2; a.Wo = (W + 1) / 2;
     a.vec_in = ((reinterpret_cast<uintptr_t>(src) | sp | sstride) % 16 == 0) ? 1 : 0;
     a.vec_out = ((reinterpret_cast<uintptr_t>(dst) | dp | dstride) % 8 == 0) ? 1 : 0;
-    constexpr int smem = kPyrInRows * kPyrInPitch;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(pyr_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
+    if (a.Ho >= 512) {
+        constexpr int TY = 64, smem = (2 * TY + 3) * kPyrInPitch;
+        dim3 grid((a.Wo + kPyrTileX - 1) / kPyrTileX, (a.Ho + TY - 1) / TY, n);
+        pyr_down_kernel<TY><<<grid, (kPyrTileX / 8) * (TY / kPyrRY), smem, stream>>>(a);
+    } else {
+        constexpr int TY = 32, smem = (2 * TY + 3) * kPyrInPitch;
+        dim3 grid((a.Wo + kPyrTileX - 1) / kPyrTileX, (a.Ho + TY - 1) / TY, n);
+        pyr_down_kernel<TY><<<grid, (kPyrTileX / 8) * (TY / kPyrRY), smem, stream>>>(a);
     }
-    dim3 grid((a.Wo + kPyrTileX - 1) / kPyrTileX, (a.Ho + kPyrTileY - 1) / kPyrTileY, n);
-    pyr_down_kernel<<<grid, kPyrThreads, smem, stream>>>(a);
     note_launch();
     return check_launch("pyr_down_kernel");
 }
