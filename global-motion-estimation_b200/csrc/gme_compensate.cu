@@ -166,6 +166,99 @@ __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
     if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + plane);
 }
 
+// The case the pipeline runs (results.py:52-59): 16 x 16 blocks (BBME_BLOCK_SIZE), 16-byte aligned planes.  Same
+// arithmetic as compensate_kernel, stripped to what this case needs: the 16-pixel run of a thread is exactly one
+// block column, the four rows of a thread share the block row, all index math is shifts, and the row pointers are
+// walked instead of recomputed.  Runs whose source leaves the frame go through the per-byte blend.
+template <bool HAS_CUR>
+__global__ void __launch_bounds__(256) compensate16_kernel(CompArgs a)
+{
+    const int plane = blockIdx.z;
+    const int row0 = (blockIdx.y * 8 + threadIdx.y) * kCompRows;
+    const int b0 = (blockIdx.x * 32 + threadIdx.x) * 16;
+    unsigned int err = 0;
+    if (row0 < a.H && b0 + 16 <= a.W) {
+        const uint8_t *fplane = a.frame + (size_t)plane * a.fstride;
+        const int i = row0 >> 4, j0 = b0 >> 4;
+        int lo = 16, hi = 0, d1 = 0, s0 = 0;                                 // bytes [lo, hi) of a run are moved
+        if (i < a.R && j0 < a.C) {
+            int d0;
+            load_vector(a, plane, i, j0, d0, d1);
+            d0 = clampi(d0, -(1 << 24), 1 << 24);
+            d1 = clampi(d1, -(1 << 24), 1 << 24);
+            s0 = b0 - d0;                                                    // motion.py:313
+            lo = max(0, -s0);
+            hi = min(16, a.W - s0);
+        }
+        const bool whole = lo == 0 && hi == 16;                              // the common case: the run moves as a whole
+        const int sa = s0 & ~3;
+        const int sh = (s0 - sa) * 8;
+        const bool inside = sa >= 0 && sa + 20 <= (int)a.fp;
+        const uint8_t *orig = fplane + (size_t)row0 * a.fp + b0;
+        const uint8_t *crow = HAS_CUR ? a.cur + (size_t)plane * a.cstride + (size_t)row0 * a.cp + b0 : nullptr;
+        uint8_t *orow = a.comp + (size_t)plane * a.ostride + (size_t)row0 * a.op + b0;
+        const int nrows = min(kCompRows, a.H - row0);
+        const int na0 = row0 - d1;                                           // motion.py:312
+        uint32_t px[kCompRows][4];
+        uint4 cur4[kCompRows];
+        if (whole && inside && na0 >= 0 && na0 + kCompRows <= a.H && nrows == kCompRows) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(fplane + (size_t)na0 * a.fp + sa);
+            const size_t fpw = a.fp >> 2;
+#pragma unroll
+            for (int r = 0; r < kCompRows; r++) {
+                uint32_t w[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) w[k] = __ldg(src + r * fpw + k);
+#pragma unroll
+                for (int k = 0; k < 4; k++) px[r][k] = __funnelshift_r(w[k], w[k + 1], sh);
+                if (HAS_CUR) cur4[r] = *reinterpret_cast<const uint4 *>(crow + (size_t)r * a.cp);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kCompRows; r++) {
+                if (r < nrows) {
+                    const int na = na0 + r;
+                    const bool moved = lo < hi && na >= 0 && na < a.H;
+                    if (moved) {
+                        const uint8_t *srow = fplane + (size_t)na * a.fp;
+                        uint32_t w[5];
+#pragma unroll
+                        for (int k = 0; k < 5; k++) {
+                            const int c = sa + 4 * k;
+                            w[k] = (c >= 0 && c + 4 <= (int)a.fp) ? __ldg(reinterpret_cast<const uint32_t *>(srow + c)) : 0u;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++) px[r][k] = __funnelshift_r(w[k], w[k + 1], sh);
+                    }
+                    if (!moved || !whole) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(orig + (size_t)r * a.fp);
+                        const uint32_t o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t m = moved ? (byte_mask(clampi(hi - 4 * k, 0, 4)) & ~byte_mask(clampi(lo - 4 * k, 0, 4))) : 0u;
+                            px[r][k] = (moved ? (px[r][k] & m) : 0u) | (o[k] & ~m);
+                        }
+                    }
+                    if (HAS_CUR) cur4[r] = *reinterpret_cast<const uint4 *>(crow + (size_t)r * a.cp);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kCompRows; r++) {
+            if (r < nrows) {
+                *reinterpret_cast<uint4 *>(orow + (size_t)r * a.op) = make_uint4(px[r][0], px[r][1], px[r][2], px[r][3]);
+                if (HAS_CUR) {
+                    err = ssd4_acc(px[r][0], cur4[r].x, err);
+                    err = ssd4_acc(px[r][1], cur4[r].y, err);
+                    err = ssd4_acc(px[r][2], cur4[r].z, err);
+                    err = ssd4_acc(px[r][3], cur4[r].w, err);
+                }
+            }
+        }
+    }
+    if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + plane);
+}
+
 __global__ void __launch_bounds__(256) sse_kernel(const uint8_t *x, size_t xp, size_t xstride, const uint8_t *y,
                                                   size_t yp, size_t ystride, int H, int W, int vec_ok,
                                                   unsigned long long *sse)
@@ -214,11 +307,14 @@ int launch_compensate(const uint8_t *frame, size_t fp, size_t fstride, const voi
     a.sse = reinterpret_cast<unsigned long long *>(sse);
     dim3 block(32, 8);
     dim3 grid(((W + 15) / 16 + block.x - 1) / block.x, (H + block.y * kCompRows - 1) / (block.y * kCompRows), n);
+    const bool lean = a.vec_ok && a.bs == 16 && W % 16 == 0;      // the pipeline's case
     if (cur && sse) {
         cudaMemsetAsync(sse, 0, sizeof(uint64_t) * n, stream);
-        compensate_kernel<true><<<grid, block, 0, stream>>>(a);
+        if (lean) compensate16_kernel<true><<<grid, block, 0, stream>>>(a);
+        else compensate_kernel<true><<<grid, block, 0, stream>>>(a);
     } else {
-        compensate_kernel<false><<<grid, block, 0, stream>>>(a);
+        if (lean) compensate16_kernel<false><<<grid, block, 0, stream>>>(a);
+        else compensate_kernel<false><<<grid, block, 0, stream>>>(a);
     }
     note_launch();
     return check_launch("compensate_kernel");
