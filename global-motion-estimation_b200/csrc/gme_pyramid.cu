@@ -67,7 +67,7 @@ __device__ __forceinline__ void hrow(const uint8_t *row, int c0, uint32_t (&h)[4
     for (int q = 0; q < 4; q++) {
         const uint32_t even = __dp4a(s[q], kTaps, __dp4a(s[q + 1], kLast, 0u));        // output 2q: bytes c0+4q-2 ..
         const uint32_t odd = __dp4a(w[q + 1], kTaps, __dp4a(w[q + 2], kLast, 0u));     // output 2q+1: bytes c0+4q ..
-        h[q] = even | (odd << 16);
+        h[q] = __byte_perm(even, odd, 0x5410);                                         // (even, odd) as 16-bit halves
     }
 }
 
@@ -154,34 +154,32 @@ __global__ void __launch_bounds__((kPyrTileX / 8) * (kPyrTileY / kPyrRY)) pyr_do
     if (ox0 >= a.Wo || oy0 >= a.Ho) return;
     const int c0 = 16 + tx * 16;                      // tile byte of the first output's centre
     const uint8_t *trow = tile + (size_t)(2 * ty * kPyrRY) * kPyrInPitch;   // tile row of image row 2*oy0 - 2
-    const bool full = ox0 + 8 <= a.Wo;
+    uint8_t *out = dplane + (size_t)oy0 * a.dp + ox0;
+    // the thread's 8 x kPyrRY outputs all exist and the rows can be stored as 8-byte words: no per-row checks
+    const bool whole = ox0 + 8 <= a.Wo && oy0 + kPyrRY <= a.Ho && a.vec_out;
 
     uint32_t hw[5][4];
 #pragma unroll
     for (int i = 0; i < 3; i++) hrow(trow + i * kPyrInPitch, c0, hw[i + 2]);
 #pragma unroll
     for (int t = 0; t < kPyrRY; t++) {
-        const int oy = oy0 + t;
-        if (oy >= a.Ho) break;
+        if (!whole && oy0 + t >= a.Ho) break;
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) hw[i][j] = hw[i + 2][j];
         hrow(trow + (2 * t + 3) * kPyrInPitch, c0, hw[3]);
         hrow(trow + (2 * t + 4) * kPyrInPitch, c0, hw[4]);
-        uint32_t t2[4];
+        uint32_t s[4];   // packed pairs of (5x5 sum + 128): the result pixel is the HIGH byte of each 16-bit half
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t s = hw[0][j] + hw[4][j] + 4u * (hw[1][j] + hw[3][j]) + 6u * hw[2][j] + 0x00800080u;
-            t2[j] = (s >> 8) & 0x00FF00FFu;
-        }
-        const uint32_t lo = __byte_perm(t2[0], t2[1], 0x6420), hi = __byte_perm(t2[2], t2[3], 0x6420);
-        uint8_t *out = dplane + (size_t)oy * a.dp + ox0;
-        if (full && a.vec_out) {
-            *reinterpret_cast<uint2 *>(out) = make_uint2(lo, hi);
+        for (int j = 0; j < 4; j++)
+            s[j] = (hw[0][j] + hw[4][j] + 0x00800080u) + 4u * (hw[1][j] + hw[3][j]) + 6u * hw[2][j];
+        const uint32_t lo = __byte_perm(s[0], s[1], 0x7531), hi = __byte_perm(s[2], s[3], 0x7531);
+        if (whole) {
+            *reinterpret_cast<uint2 *>(out + (size_t)t * a.dp) = make_uint2(lo, hi);
         } else {
             const int nvalid = min(8, a.Wo - ox0);
-            for (int k = 0; k < nvalid; k++) out[k] = (uint8_t)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xFF);
+            for (int k = 0; k < nvalid; k++) out[(size_t)t * a.dp + k] = (uint8_t)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xFF);
         }
     }
 }
