@@ -494,8 +494,11 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
     constexpr int SR[5] = {0, 0, 1, 0, -1};                    // SDSP as applied (swapped), bbme.py:474-480,518-521
     constexpr int SC[5] = {0, 1, 0, -1, 0};
     // the same tables as nibbles (value + 2), for lookups by a run-time index without a local-memory array
-    constexpr unsigned long long LRP = 0x321012342ull, LCP = 0x101234322ull;
-    constexpr unsigned SRP = 0x12322u, SCP = 0x21232u;
+    // (3 bits per entry, value + 2, entry k at bit 3k: one 32-bit constant per table)
+    constexpr unsigned LRP = 2u | (4u << 3) | (3u << 6) | (2u << 9) | (1u << 12) | (0u << 15) | (1u << 18) | (2u << 21) | (3u << 24);
+    constexpr unsigned LCP = 2u | (2u << 3) | (3u << 6) | (4u << 9) | (3u << 12) | (2u << 15) | (1u << 18) | (0u << 21) | (1u << 24);
+    constexpr unsigned SRP = 2u | (2u << 3) | (3u << 6) | (2u << 9) | (1u << 12);
+    constexpr unsigned SCP = 2u | (3u << 3) | (2u << 6) | (1u << 9) | (2u << 12);
     const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
     // centres for which the register path applies: no clamp can act on the 5 x 5 neighbourhood of offsets, and the
     // 20 x 20 pixel neighbourhood (read as 6 aligned words) lies inside the staged window
@@ -513,15 +516,16 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
 
         // anchor rows for the register path: anc[d] = anchor row lane - d, scored when a candidate has dr = d - 2;
         // msk[d] zeroes the contribution of lanes whose row lies outside that candidate
-        uint32_t anc[5][4], msk[5];
+        // (the rows themselves stay in shared memory and are re-read per candidate with one LDS.128: twenty fewer
+        // live registers keep the loop-invariant values of the walk in registers at three CTAs per SM.  Lanes whose
+        // row lies outside a candidate read some in-bounds row -- the tile is padded -- and are masked.)
+        uint32_t msk[5];
 #pragma unroll
         for (int d = 0; d < 5; d++) {
             const int k = lane - d;
-            const bool ok = lane < 20 && k >= 0 && k < BS;
-            const uint4 v = *reinterpret_cast<const uint4 *>(anchor0 + clampi(k, 0, BS - 1) * APITCH);
-            anc[d][0] = v.x; anc[d][1] = v.y; anc[d][2] = v.z; anc[d][3] = v.w;
-            msk[d] = ok ? 1u : 0u;
+            msk[d] = (lane < 20 && k >= 0 && k < BS) ? 1u : 0u;
         }
+        const uint32_t anc_addr = smem_u32(anchor0) + (uint32_t)(lane * APITCH);      // anchor row `lane`; row lane - d is d rows up
 
         uint32_t z[5] = {0, 0, 0, 0, 0};   // bytes 0..19 of this lane's neighbourhood row; byte 0 = image column mc - 2
         auto load_region = [&](int mr, int mc) {
@@ -538,9 +542,12 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
         };
         // cost of the candidate at column offset dc (the shifted words s) and row offset dr = d - 2
         auto cand = [&](const uint32_t (&s)[4], int d) -> uint32_t {
+            uint32_t an[4];
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(an[0]), "=r"(an[1]), "=r"(an[2]), "=r"(an[3]) : "r"(anc_addr - (uint32_t)(d * APITCH)));
             uint32_t acc = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) acc = cost4_acc<PNORM>(s[i], anc[d][i], acc);
+            for (int i = 0; i < 4; i++) acc = cost4_acc<PNORM>(s[i], an[i], acc);
             return __reduce_add_sync(0xFFFFFFFFu, acc * msk[d]);     // msk: 0 / 1 (IMAD: the FMA pipe has room, the ALU pipe does not)
         };
         auto shifted = [&](int bits, uint32_t (&s)[4]) {
@@ -646,8 +653,8 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
                 for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
                 kb = (int)(key & 15u);
                 if (kb == 0) { last_fast = true; break; }          // the centre wins: positions are distinct here
-                mr += (int)((LRP >> (4 * kb)) & 15) - 2;
-                mc += (int)((LCP >> (4 * kb)) & 15) - 2;
+                mr += (int)((LRP >> (3 * kb)) & 7u) - 2;
+                mc += (int)((LCP >> (3 * kb)) & 7u) - 2;
                 have = true;
             } else {
                 e.load_anchor(prev_plane, br, bc);
@@ -683,8 +690,8 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
             key = min(key, (cand(sm, 2) << 4) | 3u);               // (0, -1)
             key = min(key, (cand(s0, 1) << 4) | 4u);               // (-1, 0)
             const int ks = (int)(key & 15u);
-            out_r = mr + (int)((SRP >> (4 * ks)) & 15) - 2;
-            out_c = mc + (int)((SCP >> (4 * ks)) & 15) - 2;
+            out_r = mr + (int)((SRP >> (3 * ks)) & 7u) - 2;
+            out_c = mc + (int)((SCP >> (3 * ks)) & 7u) - 2;
         } else {
             e.load_anchor(prev_plane, br, bc);
             int r[5], cc[5];
@@ -972,7 +979,7 @@ static int launch_diamond16(PatternArgs a, int n, cudaStream_t stream)
                  make_plane_tensor_map(&pmap, a.prev, n, a.H, a.W, a.pitch, a.prev_stride, 144, tby * BS)) ? 1 : 0;
     if (!a.use_tma) { memset(&map, 0, sizeof(map)); memset(&pmap, 0, sizeof(pmap)); }
     // window (+64: the register path reads 36 bytes from a 16-byte boundary), then the anchor tile (144 x 64)
-    const size_t smem = (((size_t)win_w * win_h + 64 + 127) & ~(size_t)127) + (size_t)144 * tby * BS;
+    const size_t smem = (((size_t)win_w * win_h + 64 + 127) & ~(size_t)127) + (size_t)144 * (tby * BS + 32);   // + 32 padding rows
     auto kern = bbme_diamond16_kernel<PNORM, NT>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
