@@ -120,7 +120,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv is not None:
@@ -258,8 +258,8 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gme_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
@@ -445,7 +445,11 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(dom)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["algorithmic_gbs"], "peak": hbm_peak,
+    kernel_names = {"pyramids": "pyr_down_kernel", "bbme_dense_l0": "bbme_diamond2_kernel",
+                    "bbme_l1": "bbme_diamond16_kernel" if procedure == 3 else "bbme_exhaustive2_kernel" if procedure == 0 else "bbme_pattern_kernel",
+                    "bbme_l2": "bbme_diamond16_kernel" if procedure == 3 else "bbme_exhaustive2_kernel" if procedure == 0 else "bbme_pattern_kernel",
+                    "fit": "affine_fit_kernel", "compensate_psnr": "compensate16_kernel"}
+    roofline = {"bound": "hbm", "kernel": dom, "kernel_name": kernel_names[dom], "achieved": stages[dom]["algorithmic_gbs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": stages[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_ps[dom],
                 "whole_step_algorithmic_gbs": sum(bytes_ps.values()) / (ms_total / args.steps * 1e-3) / 1e9}
