@@ -1,9 +1,13 @@
 """GPU: the drop-in modules (bbme / motion / utils with the reference's names and signatures) against
 the reference's golden outputs -- these read like calls into the reference itself."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PARAM_TOL = dict(atol=1e-9, rtol=1e-9)
 
@@ -100,3 +104,88 @@ def test_motion_api(mods, golden, name):
     np.testing.assert_allclose(motion.affine_model(2, 3, params),
                                [params[0] + 2 * params[1] + 3 * params[2], params[3] + 2 * params[4] + 3 * params[5]],
                                rtol=1e-14, atol=0)
+
+
+def test_bbme_cli_on_a_lossless_clip(mods, tmp_path, monkeypatch):
+    """Config 2 through the reference's CLI surface (bbme.py:617-712): frames fi-3 and fi of a lossless clip, diamond,
+    bs 16 -- the two PNGs must be the needle diagrams of the oracle's fields.  Also pins the CLI quirk that -pn is
+    parsed but never forwarded (always MSE)."""
+    import cv2
+    import gme_oracle as O
+    import gme_synth as S
+    utils, bbme, motion = mods
+    seq = S.pan_sequence(6, 240, 320, step=(2, 1), seed=6)        # a geometry the reference own wrapper accepts
+    clip = str(tmp_path / "clip.avi")
+    writer = cv2.VideoWriter(clip, cv2.VideoWriter_fourcc(*"FFV1"), 30, (320, 240), isColor=True)
+    if not writer.isOpened():
+        pytest.skip("no lossless (FFV1) video writer in this OpenCV build")
+    for f in seq:
+        writer.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    writer.release()
+    frames = utils.get_video_frames(clip)
+    if len(frames) != 6 or not all(np.array_equal(a, b) for a, b in zip(frames, seq)):
+        pytest.skip("the clip did not decode losslessly on this box")
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("resources/images")
+    args = bbme._parser().parse_args(["-p", clip, "-fi", "4", "-pn", "0", "-bs", "16", "-sw", "16", "-sp", "3"])
+    bbme.main(args)
+    prev, cur = seq[1], seq[4]
+    flat = utils.draw_motion_field(cur, O.get_motion_field(prev, cur, 16, 16, 3, 1))          # MSE despite -pn 0
+    hier = utils.draw_motion_field(prev, O.hierarchical_wrapper(prev, cur, 16, 16, 3))
+    np.testing.assert_array_equal(cv2.imread("resources/images/3-res.png"), flat)
+    np.testing.assert_array_equal(cv2.imread("resources/images/3h-res.png"), hier)
+
+
+_RANK_WORKER = r'''
+import os, sys
+root, port, rank, world = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+sys.path[:0] = [os.path.join(root, "global-motion-estimation_b200")]
+import numpy as np, torch, torch.distributed as dist
+import gme_device as D, gme_synth as S
+from gme_distributed import run_sharded
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+seq = S.pan_sequence(10, 96, 160, step=(2, 1), seed=4)
+d, n_pairs = 3, 7
+planes = D.Planes.from_host(seq)                     # every rank holds the frames of its own pair range only in a real run
+
+def compute(start, stop):                            # this rank's contiguous pair range on the GPU
+    if stop == start:
+        return torch.zeros((0, 7), dtype=torch.float64)
+    pipe = D.Pipeline(stop - start, 96, 160)
+    pipe.run(planes.view(start, stop), planes.view(start + d, stop + d))
+    torch.cuda.synchronize()
+    rows = torch.zeros((stop - start, 7), dtype=torch.float64)
+    rows[:, :6] = pipe.params.cpu()
+    rows[:, 6] = torch.tensor([p.real if p != -1 else -1.0 for p in pipe.psnr()], dtype=torch.float64)
+    return rows
+
+rows = run_sharded(n_pairs, compute)
+if rank == 0:
+    np.save(sys.argv[5], rows.numpy())
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_pair_sharding_gives_identical_rows(world, tmp_path):
+    """SURVEY 8(e) determinism check: the gathered [pairs, 7] rows (6 parameters + PSNR) do not depend on how many
+    ranks the pairs are sharded over.  The ranks share cuda:0 here (no rank waits on another inside a kernel); the
+    collective runs over gloo, the same gather code the NCCL path uses."""
+    import socket
+    import subprocess
+    import sys as _sys
+    script = tmp_path / "rank.py"
+    script.write_text(_RANK_WORKER)
+    outs = {}
+    for w in sorted({1, world}):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        out = tmp_path / f"rows_{w}.npy"
+        procs = [subprocess.Popen([_sys.executable, str(script), ROOT, str(port), str(r), str(w), str(out)],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(w)]
+        logs = [p.communicate(timeout=300)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), logs
+        outs[w] = np.load(out)
+    np.testing.assert_array_equal(outs[world], outs[1])
+    assert outs[1].shape == (7, 7) and np.isfinite(outs[1]).all()
