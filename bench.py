@@ -315,6 +315,16 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = "unchanged"
+    try:
+        # pinned host frames should live on the NUMA node this GPU hangs off: bind the process to the GPU's ideal
+        # CPUs before the first pinned allocation (first touch decides the node)
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = "bound to the GPU's ideal CPUs (%d cores)" % len(os.sched_getaffinity(0))
+    except Exception as exc:                                                      # noqa: BLE001
+        numa = f"unchanged ({type(exc).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nf = pairs + DISTANCE
@@ -488,6 +498,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": runner.h2d_bytes,
                 "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                 "api": "gme_device.HostSequenceRunner.run(pinned uint8[frames,H,W]) -> pinned float64[pairs,8]",
+                "cpu_affinity": numa,
                 "h2d_gbs": runner.h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
         "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
         "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "bbme_exhaustive": exhaustive,

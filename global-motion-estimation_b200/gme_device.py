@@ -198,7 +198,7 @@ def psnr_from_sse(sse_value: int, npix: int):
 class Pipeline:
     """motion.global_motion_estimation + model field + compensation + PSNR for batches of n pairs.
 
-    Owns the workspace and the output buffers; ``run`` enqueues the whole pipeline (12 kernel
+    Owns the workspace and the output buffers; ``run`` enqueues the whole pipeline (7 kernel
     launches) on the current stream without any host synchronisation, so it can be captured in
     a CUDA graph (``capture``) and replayed."""
 
