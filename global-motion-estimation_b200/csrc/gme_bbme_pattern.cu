@@ -434,6 +434,8 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
     constexpr int BS = 16;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
+    __shared__ int next_block;                        // walks differ in length: warps take macroblocks from a queue
+    if (threadIdx.x == 0) next_block = NT / 32;       // (the first NT/32 are handed out statically)
 
     const int plane = blockIdx.z;
     constexpr int TBX = 8, TBY = 4;                   // macroblocks per tile (fixed: index math by shifts)
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
     const uint32_t row_base = smem_u32(smem) + (uint32_t)(Rl * a.win_w);
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
 
-    for (int b = warp; b < TBX * TBY; b += NT / 32) {
+    for (int b = warp; b < TBX * TBY; b = __shfl_sync(0xFFFFFFFFu, lane == 0 ? atomicAdd(&next_block, 1) : 0, 0)) {
         const int bi = tile_r + b / TBX, bj = tile_c + b % TBX;
         if (bi >= a.R || bj >= a.C) continue;
         const int br = bi * BS, bc = bj * BS;
