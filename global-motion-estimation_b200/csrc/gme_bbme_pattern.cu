@@ -256,26 +256,45 @@ __device__ __forceinline__ void twodlog_walk(const E &e, int bs, int sw, int H, 
     int dx = 0, dy = 0;                                        // bbme.py:371
     int x = br, y = bc;
     int step = sw;
+    // The centre of every iteration after the first is the winner of the previous one, so its cost is already
+    // known (the reference evaluates it again and gets the same number): only the other positions are scored.
+    bool have_centre = false;
+    uint32_t centre_cost = 0;
     while (step > 1) {                                         // bbme.py:381
         uint32_t best = kInfCost;
         if (step > 2) {                                        // cross, bbme.py:387-393
             int r[5] = {x, x + step, x - step, x, x};
             int c[5] = {y, y, y, y + step, y - step};
-            int pr[5], pc[5];
             bool ok[5];
             uint32_t cost[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                ok[k] = cand_in_frame(r[k], c[k], bs, H, W);
-                pr[k] = ok[k] ? r[k] : br;
-                pc[k] = ok[k] ? c[k] : bc;
+            for (int k = 0; k < 5; k++) ok[k] = cand_in_frame(r[k], c[k], bs, H, W);
+            if (have_centre) {
+                int pr[4], pc[4];
+                uint32_t c4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    pr[k] = ok[k + 1] ? r[k + 1] : br;
+                    pc[k] = ok[k + 1] ? c[k + 1] : bc;
+                }
+                e.template eval<4>(pr, pc, c4);
+                cost[0] = centre_cost;
+#pragma unroll
+                for (int k = 0; k < 4; k++) cost[k + 1] = c4[k];
+            } else {
+                int pr[5], pc[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    pr[k] = ok[k] ? r[k] : br;
+                    pc[k] = ok[k] ? c[k] : bc;
+                }
+                e.template eval<5>(pr, pc, cost);
             }
-            e.template eval<5>(pr, pc, cost);
 #pragma unroll
             for (int k = 0; k < 5; k++)
                 if (ok[k] && cost[k] < best) { best = cost[k]; dx = r[k]; dy = c[k]; }
         } else {                                               // step == 2: 3x3, row outer (bbme.py:394-398)
-            int r[9], c[9], pr[9], pc[9];
+            int r[9], c[9];
             bool ok[9];
             uint32_t cost[9];
 #pragma unroll
@@ -283,10 +302,29 @@ __device__ __forceinline__ void twodlog_walk(const E &e, int bs, int sw, int H, 
                 r[k] = x + (k / 3 - 1) * 2;
                 c[k] = y + (k % 3 - 1) * 2;
                 ok[k] = cand_in_frame(r[k], c[k], bs, H, W);
-                pr[k] = ok[k] ? r[k] : br;
-                pc[k] = ok[k] ? c[k] : bc;
             }
-            e.template eval<9>(pr, pc, cost);
+            if (have_centre) {
+                int pr[8], pc[8];
+                uint32_t c8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int q = k < 4 ? k : k + 1;           // every position but the centre (index 4)
+                    pr[k] = ok[q] ? r[q] : br;
+                    pc[k] = ok[q] ? c[q] : bc;
+                }
+                e.template eval<8>(pr, pc, c8);
+#pragma unroll
+                for (int k = 0; k < 8; k++) cost[k < 4 ? k : k + 1] = c8[k];
+                cost[4] = centre_cost;
+            } else {
+                int pr[9], pc[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    pr[k] = ok[k] ? r[k] : br;
+                    pc[k] = ok[k] ? c[k] : bc;
+                }
+                e.template eval<9>(pr, pc, cost);
+            }
 #pragma unroll
             for (int k = 0; k < 9; k++)
                 if (ok[k] && cost[k] < best) { best = cost[k]; dx = r[k]; dy = c[k]; }
@@ -294,6 +332,8 @@ __device__ __forceinline__ void twodlog_walk(const E &e, int bs, int sw, int H, 
         if ((dx == x && dy == y) || step == 2) step /= 2;      // bbme.py:423-425
         x = dx;
         y = dy;
+        have_centre = best != kInfCost;                        // (x, y) is now the position that scored `best`
+        centre_cost = best;
     }
     out1 = dx - br;                                            // bbme.py:430-431 (-position when the loop never ran)
     out0 = dy - bc;
