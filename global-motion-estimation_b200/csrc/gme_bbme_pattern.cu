@@ -125,9 +125,13 @@ struct BlockEval {
 
     __device__ __forceinline__ uint32_t reduce(uint32_t v) const
     {
+        if constexpr (G == 32) {
+            return __reduce_add_sync(0xFFFFFFFFu, v);        // one REDUX.SUM instead of five shuffle steps
+        } else {
 #pragma unroll
-        for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-        return v;
+            for (int o = G / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+            return v;
+        }
     }
 
     // costs of N candidates; all loads are issued before the reductions (ILP)
@@ -1064,7 +1068,7 @@ static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
     case 4: return launch_fast<4, 1, PNORM>(a, n, stream);
     case 8: return launch_fast<8, 4, PNORM>(a, n, stream);
     case 12: return launch_fast<12, 4, PNORM>(a, n, stream);
-    case 16: return launch_fast<16, 16, PNORM>(a, n, stream);    // (a warp per macroblock, G = 32, measured 25 % slower)
+    case 16: return launch_fast<16, 16, PNORM>(a, n, stream);    // (a warp per macroblock, G = 32, measured 2-10 % slower)
     default: break;
     }
     if (a.sums) return GME_ERR_UNSUPPORTED;              // channel sums are only produced by the tiled kernel
