@@ -1,0 +1,77 @@
+"""GPU: seeded random geometries against the oracle -- frame sizes that are not multiples of anything, windows
+larger than the frame, flat and tie-heavy content, every procedure / norm / tiled block size, and whole pipelines."""
+import numpy as np
+import pytest
+import torch
+
+import gme_oracle as O
+import gme_synth as S
+
+pytestmark = pytest.mark.gpu
+
+import os
+
+PARAM_TOL = dict(atol=1e-9, rtol=1e-9)
+SCALE = int(os.environ.get("GME_FUZZ_SCALE", "1"))       # GME_FUZZ_SCALE=20 for a long soak run
+
+
+@pytest.fixture(scope="module")
+def D():
+    import gme_device
+    gme_device.require_cuda()
+    return gme_device
+
+
+def _content(rng, H, W, kind):
+    if kind == 0:                                         # smooth texture, small pan
+        base = S.texture(H + 16, W + 16, seed=int(rng.integers(1 << 30)))
+        dy, dx = (int(v) for v in rng.integers(-6, 7, 2))
+        return (np.ascontiguousarray(base[8:8 + H, 8:8 + W]),
+                np.ascontiguousarray(base[8 - dy:8 - dy + H, 8 - dx:8 - dx + W]))
+    if kind == 1:                                         # white noise: many local minima
+        return (rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8))
+    if kind == 2:                                         # few grey levels: ties everywhere
+        a = (rng.integers(0, 3, (H, W)) * 100).astype(np.uint8)
+        return a, np.roll(a, (int(rng.integers(-3, 4)), int(rng.integers(-3, 4))), (0, 1))
+    flat = np.full((H, W), int(rng.integers(0, 256)), np.uint8)        # constant: every cost ties
+    return flat, flat.copy()
+
+
+@pytest.mark.parametrize("seed", range(12 * SCALE))
+def test_bbme_fuzz(D, seed):
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(6):
+        bs = int(rng.choice([2, 4, 8, 12, 16, 16, 16, 5, 20]))
+        H = int(rng.integers(bs + 1, 150))
+        W = int(rng.integers(bs + 1, 200))
+        sw = int(rng.integers(0, 20))
+        prev, cur = _content(rng, H, W, int(rng.integers(0, 4)))
+        pp, cp = D.Planes.from_host(prev), D.Planes.from_host(cur)
+        for sp in range(4):
+            pn = int(rng.integers(0, 2))
+            if bs > 16 and pn == 1:
+                pn = 0                                    # SSD beyond bs 16 is float32-rounded in the reference
+            got = D.motion_field(pp, cp, bs, sw, sp, pn)[0].cpu().numpy()
+            want = O.get_motion_field(prev, cur, bs, sw, sp, pn)
+            np.testing.assert_array_equal(got, want, err_msg=f"H={H} W={W} bs={bs} sw={sw} sp={sp} pn={pn}")
+
+
+@pytest.mark.parametrize("seed", range(6 * SCALE))
+def test_pipeline_fuzz(D, seed):
+    rng = np.random.default_rng(2000 + seed)
+    H, W = int(rng.integers(140, 400)), int(rng.integers(140, 520))      # both levels need at least one 16 x 16 block
+    n, d = 3, int(rng.integers(1, 3))
+    seq = S.zoom_rotate_sequence(n + d, H, W, zoom_per_frame=float(rng.uniform(0, 0.01)),
+                                 deg_per_frame=float(rng.uniform(-0.5, 0.5)), seed=int(rng.integers(1 << 30)))
+    sp, sw = [(3, 2), (1, 7), (2, 9), (0, 5)][seed % 4]
+    pipe = D.gme_sequence(D.Planes.from_host(seq), d, procedure=sp, window=sw)
+    torch.cuda.synchronize()
+    for k in range(n):
+        want, inter = O.global_motion_estimation(seq[k], seq[k + d], procedure=sp, window=sw, return_intermediates=True)
+        np.testing.assert_array_equal(pipe.intermediate(0)[k].cpu().numpy(), inter[0]["dense"])
+        np.testing.assert_array_equal(pipe.intermediate(2)[k].cpu().numpy(), inter[2]["gt"])
+        np.testing.assert_array_equal(pipe.intermediate(4)[k].cpu().numpy().astype(bool), inter[2]["outlier"])
+        np.testing.assert_allclose(pipe.params[k].cpu().numpy(), want, **PARAM_TOL)
+        comp = O.compensate_frame(seq[k], O.get_motion_field_affine((H // 16, W // 16), want))
+        np.testing.assert_array_equal(pipe.comp.to_host()[k], comp)
+        assert int(pipe.sse[k].item()) == O.sse(seq[k + d], comp)
