@@ -358,11 +358,9 @@ def main():
             if world > 1:
                 GD.gather_rows(runner.dev_rows[:, :7], total_pairs)
             return out
-        pipe.run(prev, cur, procedure, window)
-        out = rows()
-        if world > 1:
-            GD.gather_rows(out[:, :7], total_pairs)
-        return out
+        pipe.run(prev, cur, procedure, window)          # results: pipe.params / pipe.sse / pipe.status / pipe.comp (device)
+        if world > 1:                                   # the only exchange of the path: [pairs, 7] rows to every rank
+            GD.gather_rows(rows()[:, :7], total_pairs)
 
     def barrier():
         if world > 1:
