@@ -88,7 +88,23 @@ def rescale_motion_field(motion_field, scale=2):
 
 
 def hierarchical_wrapper(previous, current, block_size=10, search_window=4, searching_procedure=3):
-    """bbme.py:549-605 -- three-level BBME, each finer level averaged with the upsampled coarser one."""
+    """bbme.py:549-605 -- three-level BBME, each finer level averaged with the upsampled coarser one -> float64.
+
+    When the level shapes merge the way bbme.py:596-604 expects, everything (pyramids, the three searches, the two
+    merges) runs on the device with one upload and one download; odd geometries take the step-by-step host path
+    below, which raises or broadcasts exactly like the reference's NumPy code."""
+    prev, cur = np.asarray(previous), np.asarray(current)
+    if prev.ndim == 2 and prev.shape == cur.shape and block_size > 0 and 0 <= searching_procedure <= 3:
+        shapes = []
+        h, w = prev.shape
+        for _ in range(3):
+            shapes.insert(0, (int(h / block_size), int(w / block_size)))
+            h, w = (h + 1) // 2, (w + 1) // 2
+        if all(r > 0 and c > 0 for r, c in shapes) and all(
+                _dev.hierarchical_shapes_merge(a, b) for a, b in zip(shapes, shapes[1:])):
+            out = _dev.hierarchical_field(_dev.Planes.from_host(prev), _dev.Planes.from_host(cur), block_size,
+                                          search_window, searching_procedure)
+            return out[0].cpu().numpy()
     previous_pyr = get_pyramids(previous, levels=3)
     current_pyr = get_pyramids(current, levels=3)
     motion_field = get_motion_field(previous_pyr[0], current_pyr[0], block_size=block_size,

@@ -25,7 +25,9 @@ int launch_affine_field(const double *, int, int, int, int16_t *, cudaStream_t);
 int launch_pipeline_fits(const int32_t *, int, int, int, int, uint8_t *, const int32_t *, int, int, int, int, uint8_t *,
                          int, double, double *, int32_t *, const long long *, long, int16_t *, cudaStream_t);
 int launch_compensate(const uint8_t *, size_t, size_t, const void *, int, int, int, const uint8_t *, size_t, size_t,
-                      uint8_t *, size_t, size_t, int, int, int, uint64_t *, cudaStream_t);
+                      uint8_t *, size_t, size_t, int, int, int, uint64_t *, cudaStream_t, uint8_t * = nullptr,
+                      uint8_t * = nullptr, size_t = 0, size_t = 0);
+int launch_hier_merge(const void *, int, int, int, const int32_t *, int, int, int, double *, cudaStream_t);
 int launch_sse(const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t, int, int, int, uint64_t *,
                cudaStream_t);
 
@@ -293,6 +295,34 @@ int gme_compensate(const uint8_t *frame, size_t frame_pitch, size_t frame_plane_
     return launch_compensate(frame, frame_pitch, frame_plane_stride, field, field_is_i16, R, C, cur, cur_pitch,
                              cur_plane_stride, comp, comp_pitch, comp_plane_stride, n, H, W, sse,
                              static_cast<cudaStream_t>(stream));
+}
+
+int gme_compensate_diffs(const uint8_t *frame, size_t frame_pitch, size_t frame_plane_stride, const void *field,
+                         int field_is_i16, int R, int C, const uint8_t *cur, size_t cur_pitch, size_t cur_plane_stride,
+                         uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride, uint8_t *diff_prev, uint8_t *diff_comp,
+                         size_t diff_pitch, size_t diff_plane_stride, int n, int H, int W, uint64_t *sse, void *stream)
+{
+    if (!frame || !comp || !cur || !sse || !diff_prev || !diff_comp || n < 0 || H <= 0 || W <= 0 || R < 0 || C < 0)
+        return GME_ERR_INVALID_ARGUMENT;
+    if (!field && R * C > 0) return GME_ERR_INVALID_ARGUMENT;
+    if (diff_pitch < (size_t)W) return GME_ERR_INVALID_ARGUMENT;
+    if (frame_pitch % 4 || (reinterpret_cast<uintptr_t>(frame) % 4) || frame_plane_stride % 4) return GME_ERR_ALIGNMENT;
+    if (n == 0) return GME_OK;
+    return launch_compensate(frame, frame_pitch, frame_plane_stride, field, field_is_i16, R, C, cur, cur_pitch,
+                             cur_plane_stride, comp, comp_pitch, comp_plane_stride, n, H, W, sse,
+                             static_cast<cudaStream_t>(stream), diff_prev, diff_comp, diff_pitch, diff_plane_stride);
+}
+
+int gme_hier_merge(const void *coarse, int coarse_is_f64, int Rc, int Cc, const int32_t *fine, int R, int C, int n,
+                   double *out, void *stream)
+{
+    if (!coarse || !fine || !out || n < 0 || Rc <= 0 || Cc <= 0 || R <= 0 || C <= 0) return GME_ERR_INVALID_ARGUMENT;
+    // bbme.py:596-602: the upsampled field gets ONE zero row, or else ONE zero column, when the shapes differ; anything
+    // else does not broadcast in the reference (it raises), so it is not a geometry this entry point accepts
+    const bool same = (2 * Rc == R && 2 * Cc == C), row = (2 * Rc + 1 == R && 2 * Cc == C), col = (2 * Rc == R && 2 * Cc + 1 == C);
+    if (!(same || row || col)) return GME_ERR_UNSUPPORTED;
+    if (n == 0) return GME_OK;
+    return launch_hier_merge(coarse, coarse_is_f64, Rc, Cc, fine, R, C, n, out, static_cast<cudaStream_t>(stream));
 }
 
 int gme_sse(const uint8_t *a, size_t a_pitch, size_t a_plane_stride, const uint8_t *b, size_t b_pitch,

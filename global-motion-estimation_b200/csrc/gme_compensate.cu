@@ -23,6 +23,7 @@ struct CompArgs {
     int H, W;
     int vec_ok;
     unsigned long long *sse;
+    uint8_t *dprev, *dcomp; size_t dp, dstride;   // optional |cur - frame| and |cur - comp| planes (results.py:78-83)
 };
 
 __device__ __forceinline__ void load_vector(const CompArgs &a, int plane, int i, int j, int &d0, int &d1)
@@ -170,9 +171,10 @@ __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
 // arithmetic as compensate_kernel, stripped to what this case needs: the 16-pixel run of a thread is exactly one
 // block column, the four rows of a thread share the block row, all index math is shifts, and the row pointers are
 // walked instead of recomputed.  Runs whose source leaves the frame go through the per-byte blend.
-template <bool HAS_CUR>
+template <bool HAS_CUR, bool DIFFS>
 __global__ void __launch_bounds__(256) compensate16_kernel(CompArgs a)
 {
+    static_assert(!DIFFS || HAS_CUR, "the difference images need the current frame");
     const int plane = blockIdx.z;
     const int row0 = (blockIdx.y * 8 + threadIdx.y) * kCompRows;
     const int b0 = (blockIdx.x * 32 + threadIdx.x) * 16;
@@ -253,10 +255,33 @@ __global__ void __launch_bounds__(256) compensate16_kernel(CompArgs a)
                     err = ssd4_acc(px[r][2], cur4[r].z, err);
                     err = ssd4_acc(px[r][3], cur4[r].w, err);
                 }
+                if (DIFFS) {                                 // results.py:78-83: |current - compensated|, |current - previous|
+                    const size_t off = (size_t)plane * a.dstride + (size_t)(row0 + r) * a.dp + b0;
+                    *reinterpret_cast<uint4 *>(a.dcomp + off) = make_uint4(absdiff4(px[r][0], cur4[r].x), absdiff4(px[r][1], cur4[r].y),
+                                                                           absdiff4(px[r][2], cur4[r].z), absdiff4(px[r][3], cur4[r].w));
+                    const uint4 o = *reinterpret_cast<const uint4 *>(orig + (size_t)r * a.fp);
+                    *reinterpret_cast<uint4 *>(a.dprev + off) = make_uint4(absdiff4(o.x, cur4[r].x), absdiff4(o.y, cur4[r].y),
+                                                                           absdiff4(o.z, cur4[r].z), absdiff4(o.w, cur4[r].w));
+                }
             }
         }
     }
     if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + plane);
+}
+
+// |x - y| per pixel (the difference images of results.py:78-83 when the fused kernel does not apply)
+__global__ void __launch_bounds__(256) absdiff_kernel(const uint8_t *x, size_t xp, size_t xstride, const uint8_t *y,
+                                                      size_t yp, size_t ystride, uint8_t *out, size_t op, size_t ostride,
+                                                      int H, int W)
+{
+    const int plane = blockIdx.z;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (r >= H || c0 >= W) return;
+    const uint8_t *xr = x + (size_t)plane * xstride + (size_t)r * xp + c0;
+    const uint8_t *yr = y + (size_t)plane * ystride + (size_t)r * yp + c0;
+    uint8_t *o = out + (size_t)plane * ostride + (size_t)r * op + c0;
+    for (int k = 0; k < min(16, W - c0); k++) o[k] = (uint8_t)abs((int)xr[k] - (int)yr[k]);
 }
 
 __global__ void __launch_bounds__(256) sse_kernel(const uint8_t *x, size_t xp, size_t xstride, const uint8_t *y,
@@ -293,9 +318,11 @@ static inline bool aligned16(const void *p, size_t pitch, size_t stride)
 
 int launch_compensate(const uint8_t *frame, size_t fp, size_t fstride, const void *field, int field_is_i16, int R,
                       int C, const uint8_t *cur, size_t cp, size_t cstride, uint8_t *comp, size_t op, size_t ostride,
-                      int n, int H, int W, uint64_t *sse, cudaStream_t stream)
+                      int n, int H, int W, uint64_t *sse, cudaStream_t stream, uint8_t *dprev = nullptr,
+                      uint8_t *dcomp = nullptr, size_t dp = 0, size_t dstride = 0)
 {
     CompArgs a;
+    a.dprev = dprev; a.dcomp = dcomp; a.dp = dp; a.dstride = dstride;
     a.frame = frame; a.fp = fp; a.fstride = fstride;
     a.field = field; a.field_is_i16 = field_is_i16;
     a.bs = (R > 0) ? H / R : 0;                                   // motion.py:303: rows only
@@ -308,15 +335,25 @@ int launch_compensate(const uint8_t *frame, size_t fp, size_t fstride, const voi
     dim3 block(32, 8);
     dim3 grid(((W + 15) / 16 + block.x - 1) / block.x, (H + block.y * kCompRows - 1) / (block.y * kCompRows), n);
     const bool lean = a.vec_ok && a.bs == 16 && W % 16 == 0;      // the pipeline's case
+    const bool diffs = dprev && dcomp && cur && sse;
+    const bool fused_diffs = diffs && lean && aligned16(dprev, dp, dstride) && aligned16(dcomp, dp, dstride);
     if (cur && sse) {
         cudaMemsetAsync(sse, 0, sizeof(uint64_t) * n, stream);
-        if (lean) compensate16_kernel<true><<<grid, block, 0, stream>>>(a);
+        if (fused_diffs) compensate16_kernel<true, true><<<grid, block, 0, stream>>>(a);
+        else if (lean) compensate16_kernel<true, false><<<grid, block, 0, stream>>>(a);
         else compensate_kernel<true><<<grid, block, 0, stream>>>(a);
     } else {
-        if (lean) compensate16_kernel<false><<<grid, block, 0, stream>>>(a);
+        if (lean) compensate16_kernel<false, false><<<grid, block, 0, stream>>>(a);
         else compensate_kernel<false><<<grid, block, 0, stream>>>(a);
     }
     note_launch();
+    if (diffs && !fused_diffs) {
+        dim3 g2(((W + 15) / 16 + 31) / 32, (H + 7) / 8, n);
+        absdiff_kernel<<<g2, block, 0, stream>>>(cur, cp, cstride, frame, fp, fstride, dprev, dp, dstride, H, W);
+        absdiff_kernel<<<g2, block, 0, stream>>>(cur, cp, cstride, comp, op, ostride, dcomp, dp, dstride, H, W);
+        note_launch();
+        note_launch();
+    }
     return check_launch("compensate_kernel");
 }
 

@@ -355,6 +355,40 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
     }
 }
 
+// bbme.hierarchical_wrapper's merge step (bbme.py:587-604): the coarser field is upsampled by 2 in both axes (nearest),
+// its vectors truncated to int32 and doubled (bbme.rescale_motion_field, bbme.py:537-546), padded with one zero row or
+// column where the finer field has one more, and averaged with the finer field: out = (2*trunc(coarse) + fine) / 2.
+template <typename T>
+__global__ void hier_merge_kernel(const T *coarse, int Rc, int Cc, const int32_t *fine, int R, int C, double *out)
+{
+    const long N = (long)R * C;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N) return;
+    const int i = (int)(idx / C), j = (int)(idx % C);
+    const T *cp = coarse + (size_t)blockIdx.y * Rc * Cc * 2;
+    int u0 = 0, u1 = 0;
+    if (i / 2 < Rc && j / 2 < Cc) {
+        u0 = 2 * (int)cp[((size_t)(i / 2) * Cc + j / 2) * 2];          // (int): truncation toward zero, like ndarray assignment
+        u1 = 2 * (int)cp[((size_t)(i / 2) * Cc + j / 2) * 2 + 1];
+    }
+    const int2 f = *reinterpret_cast<const int2 *>(fine + ((size_t)blockIdx.y * N + idx) * 2);
+    double *o = out + ((size_t)blockIdx.y * N + idx) * 2;
+    o[0] = (double)(u0 + f.x) / 2.0;
+    o[1] = (double)(u1 + f.y) / 2.0;
+}
+
+int launch_hier_merge(const void *coarse, int coarse_is_f64, int Rc, int Cc, const int32_t *fine, int R, int C, int n,
+                      double *out, cudaStream_t stream)
+{
+    dim3 grid((unsigned)(((long)R * C + 255) / 256), n);
+    if (coarse_is_f64)
+        hier_merge_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double *>(coarse), Rc, Cc, fine, R, C, out);
+    else
+        hier_merge_kernel<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t *>(coarse), Rc, Cc, fine, R, C, out);
+    note_launch();
+    return check_launch("hier_merge_kernel");
+}
+
 int launch_first_params(const int32_t *dense, int n, int R, int C, double *params, cudaStream_t stream)
 {
     first_params_kernel<<<n, kFitThreads, 0, stream>>>(dense, (long)R * C, params);

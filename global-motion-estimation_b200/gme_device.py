@@ -162,14 +162,26 @@ def affine_field(params: torch.Tensor, R: int, C: int) -> torch.Tensor:
     return field
 
 
-def compensate(frame: Planes, field: torch.Tensor, cur: Planes | None = None):
-    """motion.compensate_frame for n planes; with ``cur`` also the squared error sums (int64[n])."""
+def compensate(frame: Planes, field: torch.Tensor, cur: Planes | None = None, want_diffs: bool = False):
+    """motion.compensate_frame for n planes; with ``cur`` also the squared error sums (int64[n]); with
+    ``want_diffs`` also the two difference images of results.py:78-83 (|cur - frame|, |cur - comp|)."""
     if field.dtype not in (torch.int16, torch.int32):
         raise TypeError("motion field must be int16 or int32")
     field = field.contiguous()
     n, R, C = field.shape[0], field.shape[1], field.shape[2]
     comp = Planes.empty(frame.n, frame.H, frame.W, frame.t.device)
     sse = torch.zeros((frame.n,), dtype=torch.int64, device=frame.t.device) if cur is not None else None
+    if want_diffs:
+        if cur is None:
+            raise ValueError("the difference images need the current frame")
+        dprev = Planes.empty(frame.n, frame.H, frame.W, frame.t.device)
+        dcomp = Planes.empty(frame.n, frame.H, frame.W, frame.t.device)
+        N.check(N.lib.gme_compensate_diffs(frame.ptr, frame.pitch, frame.stride, field.data_ptr(),
+                                           int(field.dtype == torch.int16), R, C, cur.ptr, cur.pitch, cur.stride,
+                                           comp.ptr, comp.pitch, comp.stride, dprev.ptr, dcomp.ptr, dprev.pitch,
+                                           dprev.stride, frame.n, frame.H, frame.W, sse.data_ptr(), _stream()),
+                "gme_compensate_diffs")
+        return comp, sse, dprev, dcomp
     N.check(N.lib.gme_compensate(frame.ptr, frame.pitch, frame.stride, field.data_ptr(),
                                  int(field.dtype == torch.int16), R, C,
                                  cur.ptr if cur is not None else None, cur.pitch if cur is not None else 0,
@@ -177,6 +189,48 @@ def compensate(frame: Planes, field: torch.Tensor, cur: Planes | None = None):
                                  frame.n, frame.H, frame.W, sse.data_ptr() if sse is not None else None, _stream()),
             "gme_compensate")
     return comp, sse
+
+
+def hierarchical_shapes_merge(coarse_shape, fine_shape) -> bool:
+    """True when bbme.hierarchical_wrapper can merge the two levels (bbme.py:596-604): the upsampled coarse field
+    equals the fine one, or lacks exactly one row, or else exactly one column."""
+    (rc, cc), (r, c) = coarse_shape, fine_shape
+    return (2 * rc, 2 * cc) == (r, c) or (2 * rc + 1, 2 * cc) == (r, c) or (2 * rc, 2 * cc + 1) == (r, c)
+
+
+def hierarchical_field(prev: Planes, cur: Planes, block_size: int, search_window: int, procedure: int) -> torch.Tensor:
+    """bbme.hierarchical_wrapper (bbme.py:549-605) for n pairs, entirely on the device: two pyramid levels per frame,
+    the coarsest field with ``procedure``, the finer two with diamond search, each merged with the upsampled coarser
+    one -> float64[n, H//bs, W//bs, 2].  Raises ValueError for geometries the reference cannot merge either."""
+    p1, c1 = pyr_down(prev), pyr_down(cur)
+    p0, c0 = pyr_down(p1), pyr_down(c1)
+    field = motion_field(p0, c0, block_size, search_window, procedure, N.PNORM_MSE)
+    for lp, lc in ((p1, c1), (prev, cur)):
+        fine = motion_field(lp, lc, block_size, search_window, N.SEARCH_DIAMOND, N.PNORM_MSE)
+        if not hierarchical_shapes_merge(field.shape[1:3], fine.shape[1:3]):
+            raise ValueError(f"operands could not be broadcast together with shapes {tuple(field.shape[1:])} {tuple(fine.shape[1:])}")
+        out = torch.empty(fine.shape, dtype=torch.float64, device=fine.device)
+        N.check(N.lib.gme_hier_merge(field.data_ptr(), int(field.dtype == torch.float64), field.shape[1], field.shape[2],
+                                     fine.data_ptr(), fine.shape[1], fine.shape[2], fine.shape[0], out.data_ptr(),
+                                     _stream()), "gme_hier_merge")
+        field = out
+    return field
+
+
+def results_batch(frames: Planes, distance: int, procedure: int = N.SEARCH_DIAMOND, window: int = 2) -> dict:
+    """Everything one iteration of the reference's results.py loop computes (results.py:47-59, 78-83, 109), for every
+    pair (k, k + distance) of a device-resident sequence, left on the device: affine parameters, model field at block
+    size 16, compensated previous frame, the two difference images and the squared-error sums behind the PSNR."""
+    n = frames.n - distance
+    if n <= 0:
+        raise ValueError("sequence shorter than the frame distance")
+    prev, cur = frames.view(0, n), frames.view(distance, distance + n)
+    pipe = Pipeline(n, frames.H, frames.W, frames.t.device, want_comp=False)
+    pipe.run(prev, cur, procedure, window)
+    model = affine_field(pipe.params, frames.H // 16, frames.W // 16)
+    comp, sse_, dprev, dcomp = compensate(prev, model, cur, want_diffs=True)
+    return {"params": pipe.params, "status": pipe.status, "model_field": model, "compensated": comp, "sse": sse_,
+            "diff_curr_prev": dprev, "diff_curr_comp": dcomp}
 
 
 def sse(a: Planes, b: Planes) -> torch.Tensor:

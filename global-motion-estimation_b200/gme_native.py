@@ -35,6 +35,8 @@ SYMBOLS = {
     "gme_affine_fit": (_i, [_p, _i, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p, _p, _p]),
     "gme_affine_field": (_i, [_p, _i, _i, _i, _p, _p]),
     "gme_compensate": (_i, [_p, _sz, _sz, _p, _i, _i, _i, _p, _sz, _sz, _p, _sz, _sz, _i, _i, _i, _p, _p]),
+    "gme_compensate_diffs": (_i, [_p, _sz, _sz, _p, _i, _i, _i, _p, _sz, _sz, _p, _sz, _sz, _p, _p, _sz, _sz, _i, _i, _i, _p, _p]),
+    "gme_hier_merge": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
     "gme_sse": (_i, [_p, _sz, _sz, _p, _sz, _sz, _i, _i, _i, _p, _p]),
     "gme_pipeline_workspace_bytes": (_sz, [_i, _i, _i]),
     "gme_pipeline": (_i, [_p, _sz, _p, _sz, _i, _i, _i, _sz, _i, _i, _p, _p, _sz, _sz, _p, _p, _p, _sz, _p]),

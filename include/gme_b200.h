@@ -104,6 +104,23 @@ GME_API int gme_compensate(const uint8_t *frame, size_t frame_pitch, size_t fram
                    uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride,
                    int n, int H, int W, uint64_t *sse, void *stream);
 
+/* gme_compensate plus the two difference images results.py writes per pair (results.py:78-83):
+ * diff_prev = |cur - frame|, diff_comp = |cur - comp| (uint8 planes sharing diff_pitch / diff_plane_stride).
+ * cur and sse are required here. */
+GME_API int gme_compensate_diffs(const uint8_t *frame, size_t frame_pitch, size_t frame_plane_stride,
+                         const void *field, int field_is_i16, int R, int C,
+                         const uint8_t *cur, size_t cur_pitch, size_t cur_plane_stride,
+                         uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride,
+                         uint8_t *diff_prev, uint8_t *diff_comp, size_t diff_pitch, size_t diff_plane_stride,
+                         int n, int H, int W, uint64_t *sse, void *stream);
+
+/* The merge step of bbme.hierarchical_wrapper (bbme.py:587-604, with rescale_motion_field, bbme.py:537-546):
+ * out[n][R][C][2] (float64) = (2 * trunc(coarse[i/2][j/2]) + fine[i][j]) / 2, the upsampled coarse field padded with one
+ * zero row or one zero column where the fine field has one more.  coarse is int32 or float64 [n][Rc][Cc][2].
+ * GME_ERR_UNSUPPORTED for shape pairs the reference itself cannot merge (it raises there). */
+GME_API int gme_hier_merge(const void *coarse, int coarse_is_f64, int Rc, int Cc,
+                   const int32_t *fine, int R, int C, int n, double *out, void *stream);
+
 /* utils.PSNR (utils.py:100-116): sse[k] = sum (a-b)^2 over plane k; the caller finishes
  * mse = sse/(H*W), 20*log10(255/sqrt(mse)). */
 GME_API int gme_sse(const uint8_t *a, size_t a_pitch, size_t a_plane_stride,

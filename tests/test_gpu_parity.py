@@ -446,3 +446,51 @@ def test_unaligned_pitch_takes_the_cooperative_paths(D):
         comp = O.compensate_frame(seq[k], O.get_motion_field_affine((H // 16, W // 16), want))
         np.testing.assert_array_equal(pipe.comp.to_host()[k], comp)
         assert int(pipe.sse[k].item()) == O.sse(seq[k + d], comp)
+
+
+# ------------------------------------------------------------------ the rows next to the hot path
+def test_results_batch_matches_the_results_loop(D):
+    """gme_device.results_batch = one iteration of results.py's loop per pair (results.py:47-59,78-83,109), with the
+    difference images fused into the compensation kernel: everything against the oracle / the NumPy formulas."""
+    H, W, d = 272, 400, 3                       # 272 = 17 * 16: the last block row exists; W % 16 == 0: fused kernel
+    seq = S.zoom_rotate_sequence(6, H, W, zoom_per_frame=0.004, deg_per_frame=0.3, seed=21)
+    out = D.results_batch(D.Planes.from_host(seq), d)
+    torch.cuda.synchronize()
+    comp, dp, dc = out["compensated"].to_host(), out["diff_curr_prev"].to_host(), out["diff_curr_comp"].to_host()
+    for k in range(seq.shape[0] - d):
+        prev, cur = seq[k], seq[k + d]
+        want = O.global_motion_estimation(prev, cur)
+        np.testing.assert_allclose(out["params"][k].cpu().numpy(), want, **PARAM_TOL)
+        model = O.get_motion_field_affine((H // 16, W // 16), want)
+        np.testing.assert_array_equal(out["model_field"][k].cpu().numpy(), model)
+        wc = O.compensate_frame(prev, model)
+        np.testing.assert_array_equal(comp[k], wc)
+        np.testing.assert_array_equal(dp[k], np.absolute(cur.astype("int") - prev.astype("int")).astype("uint8"))
+        np.testing.assert_array_equal(dc[k], np.absolute(cur.astype("int") - wc.astype("int")).astype("uint8"))
+        assert int(out["sse"][k].item()) == O.sse(cur, wc)
+    # a geometry the fused kernel does not take (W % 16 != 0): separate difference kernels, same images
+    seq2 = S.pan_sequence(5, 100, 150, step=(2, 1), seed=5)
+    out2 = D.results_batch(D.Planes.from_host(seq2), 2)
+    wc = O.compensate_frame(seq2[0], out2["model_field"][0].cpu().numpy())
+    np.testing.assert_array_equal(out2["compensated"].to_host()[0], wc)
+    np.testing.assert_array_equal(out2["diff_curr_comp"].to_host()[0],
+                                  np.absolute(seq2[2].astype("int") - wc.astype("int")).astype("uint8"))
+    np.testing.assert_array_equal(out2["diff_curr_prev"].to_host()[0],
+                                  np.absolute(seq2[2].astype("int") - seq2[0].astype("int")).astype("uint8"))
+
+
+@pytest.mark.parametrize("H,W,bs,sw,sp", [(240, 320, 12, 8, 1), (480, 720, 16, 4, 3), (250, 322, 10, 6, 0), (96, 128, 8, 5, 2)])
+def test_hierarchical_field_on_device(D, H, W, bs, sw, sp):
+    """bbme.hierarchical_wrapper with pyramids, searches and merges all on the device, batched, against the oracle."""
+    seq = S.zoom_rotate_sequence(4, H, W, zoom_per_frame=0.006, deg_per_frame=0.4, seed=H + bs)
+    planes = D.Planes.from_host(seq)
+    try:
+        want = [O.hierarchical_wrapper(seq[k], seq[k + 1], bs, sw, sp) for k in range(3)]
+    except ValueError:
+        with pytest.raises(ValueError):
+            D.hierarchical_field(planes.view(0, 3), planes.view(1, 4), bs, sw, sp)
+        return
+    got = D.hierarchical_field(planes.view(0, 3), planes.view(1, 4), bs, sw, sp).cpu().numpy()
+    assert got.dtype == np.float64
+    for k in range(3):
+        np.testing.assert_array_equal(got[k], want[k])
