@@ -110,16 +110,19 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
+    def _sample(self):
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def _loop(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
-                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+            self._sample()
             self._stop.wait(0.02)
 
     def __enter__(self):
@@ -131,6 +134,7 @@ class ClockSampler:
 
     def __exit__(self, *exc):
         if self._thread is not None:
+            self._sample()                      # at least one sample while the last kernels are still in flight
             self._stop.set()
             self._thread.join()
             self._thread = None
