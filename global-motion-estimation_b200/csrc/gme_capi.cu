@@ -33,6 +33,7 @@ int launch_sse(const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t,
 
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_last_cuda_error{0};
+static std::atomic<double> g_outlier_fraction{0.3};   // motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE (motion.py:10)
 
 // ---- per-stage timing (bench only) ----------------------------------------------------
 static std::mutex g_timing_mu;
@@ -198,6 +199,13 @@ const char *gme_error_string(int code)
 int gme_last_cuda_error(void) { return g_last_cuda_error.load(); }
 
 uint64_t gme_launch_count(void) { return g_launches.load(); }
+
+int gme_pipeline_set_outlier_fraction(double pct)
+{
+    if (!(pct >= 0.0 && pct <= 1.0)) return GME_ERR_INVALID_ARGUMENT;
+    g_outlier_fraction.store(pct);
+    return GME_OK;
+}
 
 int gme_sad_peak_probe(int pnorm, int ctas, int iters, uint32_t *scratch, uint64_t *pixel_pairs, void *stream)
 {
@@ -415,7 +423,7 @@ int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *c
     // the sequential part: first estimate, then project + robust fit per level (motion.py:128-134)
     // one launch: first estimate (mean of the dense field, from the channel sums) -> project + robust fit on L1 ->
     // project + robust fit on L2 -> model field of the final parameters at block_size 16 (results.py:52-54)
-    GME_TRY(launch_pipeline_fits(f1, L.R1, L.C1, L.l1.H, L.l1.W, out1, f2, L.R2, L.C2, H, W, out2, n, 0.3, params, status,
+    GME_TRY(launch_pipeline_fits(f1, L.R1, L.C1, L.l1.H, L.l1.W, out1, f2, L.R2, L.C2, H, W, out2, n, g_outlier_fraction.load(), params, status,
                                  reinterpret_cast<const long long *>(sums), (long)L.R0 * L.C0, comp ? model : nullptr, st));
     timer.mark();
     if (comp) {

@@ -55,6 +55,16 @@ def affine_model(x, y, parameters):
 
 def global_motion_estimation(previous, current):
     """motion.py:109-136 -- hierarchical robust affine GME of one frame pair -> float64[6]."""
+    if BBME_BLOCK_SIZE != 16:
+        # the fused pipeline is built for the reference's block size; an edited constant takes the level-by-level path
+        prev_pyr, curr_pyr = get_pyramids(previous), get_pyramids(current)
+        parameters = first_parameter_estimation(prev_pyr[0], curr_pyr[0])
+        for i in range(1, len(prev_pyr)):
+            parameters = parameter_projection(parameters)
+            parameters = best_affine_parameters_robust(prev_pyr[i], curr_pyr[i], parameters)
+        return parameters
+    _native.check(_native.lib.gme_pipeline_set_outlier_fraction(float(MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE)),
+                  "gme_pipeline_set_outlier_fraction")
     params, _, _ = _dev.gme_pairs(np.asarray(previous)[None], np.asarray(current)[None],
                                   procedure=BBME_SEARCHING_PROCEDURE, window=BBME_SEARCH_WINDOW, want_comp=False)
     return params[0]

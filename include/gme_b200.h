@@ -143,6 +143,10 @@ GME_API int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride,
                  uint64_t *sse, int32_t *status,
                  void *workspace, size_t workspace_bytes, void *stream);
 
+/* motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE (motion.py:10) as used by gme_pipeline; 0.3 unless set.  The
+ * reference keeps it as a module constant that users edit (README:137-141); the drop-in forwards its value here. */
+GME_API int gme_pipeline_set_outlier_fraction(double pct);
+
 /* Introspection for tests and the bench: pointers into a gme_pipeline workspace.
  * which: 0 dense L0 field, 1 L1 field, 2 L2 field (int32), 3 L1 outlier mask, 4 L2 outlier
  * mask (uint8), 5 model field at full resolution (int16). */

@@ -189,3 +189,33 @@ def test_pair_sharding_gives_identical_rows(world, tmp_path):
         outs[w] = np.load(out)
     np.testing.assert_array_equal(outs[world], outs[1])
     assert outs[1].shape == (7, 7) and np.isfinite(outs[1]).all()
+
+
+def test_edited_module_constants_are_honoured(mods, monkeypatch):
+    """The reference is configured by editing module constants (README:137-141).  An edited outlier percentage reaches
+    the fused pipeline; an edited block size takes the level-by-level path.  Both against the oracle."""
+    import gme_oracle as O
+    import gme_synth as S
+    utils, bbme, motion = mods
+    seq = S.zoom_rotate_sequence(2, 256, 384, zoom_per_frame=0.01, deg_per_frame=0.5, seed=17)
+    prev, cur = seq[0], seq[1]
+
+    def oracle_gme(pct):
+        ppyr, cpyr = O.get_pyramids(prev), O.get_pyramids(cur)
+        p = O.first_parameter_estimation(ppyr[0], cpyr[0])
+        for i in (1, 2):
+            p = O.parameter_projection(p)
+            gt = O.get_motion_field(ppyr[i], cpyr[i], block_size=O.BBME_BLOCK_SIZE, searching_procedure=3)
+            mask, _ = O.outlier_mask(gt, O.get_motion_field_affine(gt.shape, p), pct=pct)
+            p = O._solve(gt, mask, ppyr[i].shape)
+        return p
+
+    monkeypatch.setattr(motion, "MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE", .2)
+    np.testing.assert_allclose(motion.global_motion_estimation(prev, cur), oracle_gme(.2), **PARAM_TOL)
+    monkeypatch.setattr(motion, "MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE", .3)
+    np.testing.assert_allclose(motion.global_motion_estimation(prev, cur), oracle_gme(.3), **PARAM_TOL)
+    assert not np.allclose(oracle_gme(.2), oracle_gme(.3), atol=1e-12)           # the constant does matter here
+
+    monkeypatch.setattr(motion, "BBME_BLOCK_SIZE", 8)
+    monkeypatch.setattr(O, "BBME_BLOCK_SIZE", 8)
+    np.testing.assert_allclose(motion.global_motion_estimation(prev, cur), oracle_gme(.3), **PARAM_TOL)
