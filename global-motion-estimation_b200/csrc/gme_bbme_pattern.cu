@@ -393,7 +393,7 @@ __device__ __forceinline__ void stage_window(uint8_t *smem_win, uint64_t *bar, c
 }
 
 template <int BS, int G, int PNORM, int NT>
-__global__ void __launch_bounds__(NT) bbme_pattern_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
+__global__ void __launch_bounds__(NT, 3) bbme_pattern_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
