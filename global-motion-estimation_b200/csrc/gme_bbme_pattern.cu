@@ -163,35 +163,38 @@ __device__ __forceinline__ bool cand_in_frame(int top, int left, int bs, int H, 
     return !(top < 0 || left < 0 || top + bs - 1 > H - 1 || left + bs - 1 > W - 1);
 }
 
+// One LDSP step (bbme.py:494-513) evaluated candidate by candidate at CLAMPED positions -- the form that is always
+// valid.  Moves (mr, mc) to the first strict minimum in the reference's order; returns true when that is the centre.
 template <class E>
-__device__ __forceinline__ void diamond_walk(const E &e, int bs, int H, int W, int br, int bc, int &out0, int &out1)
+__device__ __forceinline__ bool ldsp_step_clamped(const E &e, int rmax, int cmax, int &mr, int &mc)
 {
-    // LDSP / SDSP offsets as (row, col): bbme.py:463-480; the SDSP list is applied swapped (bbme.py:518-521)
-    constexpr int LR[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};
+    constexpr int LR[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};      // LDSP offsets (row, col), bbme.py:463-472
     constexpr int LC[9] = {0, 0, 1, 2, 1, 0, -1, -2, -1};
+    int r[9], c[9];
+    uint32_t cost[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        r[k] = clampi(mr + LR[k], 0, rmax);                    // bbme.py:503-504
+        c[k] = clampi(mc + LC[k], 0, cmax);
+    }
+    e.template eval<9>(r, c, cost);
+    uint32_t best = kInfCost;
+    int best_r = mr, best_c = mc;
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+        if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = c[k]; }
+    const bool stop = (best_r == mr) && (best_c == mc);        // tuple equality, bbme.py:512
+    mr = best_r;
+    mc = best_c;
+    return stop;
+}
+
+// The final SDSP (bbme.py:515-529) at clamped positions; the offset list is applied swapped (bbme.py:518-521).
+template <class E>
+__device__ __forceinline__ void sdsp_clamped(const E &e, int rmax, int cmax, int mr, int mc, int &out_r, int &out_c)
+{
     constexpr int SR[5] = {0, 0, 1, 0, -1};
     constexpr int SC[5] = {0, 1, 0, -1, 0};
-    const int rmax = H - bs - 1, cmax = W - bs - 1;   // bbme.py:503-504 (off by one, kept)
-    int mr = br, mc = bc;
-    bool stop = false;
-    while (!stop) {                                   // bbme.py:494-513
-        int r[9], c[9];
-        uint32_t cost[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            r[k] = clampi(mr + LR[k], 0, rmax);
-            c[k] = clampi(mc + LC[k], 0, cmax);
-        }
-        e.template eval<9>(r, c, cost);
-        uint32_t best = kInfCost;
-        int best_r = mr, best_c = mc;
-#pragma unroll
-        for (int k = 0; k < 9; k++)
-            if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = c[k]; }
-        stop = (best_r == mr) && (best_c == mc);
-        mr = best_r;
-        mc = best_c;
-    }
     int r[5], c[5];
     uint32_t cost[5];
 #pragma unroll
@@ -201,10 +204,21 @@ __device__ __forceinline__ void diamond_walk(const E &e, int bs, int H, int W, i
     }
     e.template eval<5>(r, c, cost);
     uint32_t best = kInfCost;
-    int best_r = mr, best_c = mc;
+    out_r = mr;
+    out_c = mc;
 #pragma unroll
     for (int k = 0; k < 5; k++)
-        if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = c[k]; }
+        if (cost[k] < best) { best = cost[k]; out_r = r[k]; out_c = c[k]; }
+}
+
+template <class E>
+__device__ __forceinline__ void diamond_walk(const E &e, int bs, int H, int W, int br, int bc, int &out0, int &out1)
+{
+    const int rmax = H - bs - 1, cmax = W - bs - 1;   // bbme.py:503-504 (off by one, kept)
+    int mr = br, mc = bc;
+    while (!ldsp_step_clamped(e, rmax, cmax, mr, mc)) {}
+    int best_r, best_c;
+    sdsp_clamped(e, rmax, cmax, mr, mc, best_r, best_c);
     out1 = best_r - br;                               // bbme.py:531-532
     out0 = best_c - bc;
 }
@@ -535,12 +549,8 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
     e.lane_g = lane;
     e.gmask = 0xFFFFFFFFu;
 
-    constexpr int LR[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};      // LDSP offsets (row, col), bbme.py:463-472
-    constexpr int LC[9] = {0, 0, 1, 2, 1, 0, -1, -2, -1};
-    constexpr int SR[5] = {0, 0, 1, 0, -1};                    // SDSP as applied (swapped), bbme.py:474-480,518-521
-    constexpr int SC[5] = {0, 1, 0, -1, 0};
-    // the same tables as nibbles (value + 2), for lookups by a run-time index without a local-memory array
-    // (3 bits per entry, value + 2, entry k at bit 3k: one 32-bit constant per table)
+    // the LDSP / SDSP offset tables of ldsp_step_clamped / sdsp_clamped, packed for lookups by a run-time index
+    // without a local-memory array (3 bits per entry, value + 2, entry k at bit 3k)
     constexpr unsigned LRP = 2u | (4u << 3) | (3u << 6) | (2u << 9) | (1u << 12) | (0u << 15) | (1u << 18) | (2u << 21) | (3u << 24);
     constexpr unsigned LCP = 2u | (2u << 3) | (3u << 6) | (4u << 9) | (3u << 12) | (2u << 15) | (1u << 18) | (0u << 21) | (1u << 24);
     constexpr unsigned SRP = 2u | (2u << 3) | (3u << 6) | (2u << 9) | (1u << 12);
@@ -704,23 +714,8 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
                 have = true;
             } else {
                 e.load_anchor(prev_plane, br, bc);
-                int r[9], cc[9];
-                uint32_t cost[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    r[k] = clampi(mr + LR[k], 0, rmax);
-                    cc[k] = clampi(mc + LC[k], 0, cmax);
-                }
-                e.template eval<9>(r, cc, cost);
-                uint32_t best = kInfCost;
-                int best_r = mr, best_c = mc;
-#pragma unroll
-                for (int k = 0; k < 9; k++)
-                    if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = cc[k]; }
                 have = false;
-                if (best_r == mr && best_c == mc) { last_fast = false; break; }
-                mr = best_r;
-                mc = best_c;
+                if (ldsp_step_clamped(e, rmax, cmax, mr, mc)) { last_fast = false; break; }
             }
         }
 
@@ -740,20 +735,7 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_cons
             out_c = mc + (int)((SCP >> (3 * ks)) & 7u) - 2;
         } else {
             e.load_anchor(prev_plane, br, bc);
-            int r[5], cc[5];
-            uint32_t cost[5];
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                r[k] = clampi(mr + SR[k], 0, rmax);
-                cc[k] = clampi(mc + SC[k], 0, cmax);
-            }
-            e.template eval<5>(r, cc, cost);
-            uint32_t best = kInfCost;
-            out_r = mr;
-            out_c = mc;
-#pragma unroll
-            for (int k = 0; k < 5; k++)
-                if (cost[k] < best) { best = cost[k]; out_r = r[k]; out_c = cc[k]; }
+            sdsp_clamped(e, rmax, cmax, mr, mc, out_r, out_c);
         }
         if (lane == 0)
             *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(out_c - bc, out_r - br);   // bbme.py:531-532
@@ -800,10 +782,6 @@ __global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant
     e.lane_g = 0;
     e.gmask = 1u << (threadIdx.x & 31);
 
-    constexpr int LR[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};      // LDSP offsets (row, col), bbme.py:463-472
-    constexpr int LC[9] = {0, 0, 1, 2, 1, 0, -1, -2, -1};
-    constexpr int SR[5] = {0, 0, 1, 0, -1};                    // SDSP as applied (swapped), bbme.py:474-480,518-521
-    constexpr int SC[5] = {0, 1, 0, -1, 0};
     constexpr unsigned long long LRP = 0x321012342ull, LCP = 0x101234322ull;   // the same tables as nibbles (value + 2)
     constexpr unsigned SRP = 0x12322u, SCP = 0x21232u;
     const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
@@ -858,22 +836,7 @@ __global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant
                 mr += (int)((LRP >> (4 * kb)) & 15) - 2;
                 mc += (int)((LCP >> (4 * kb)) & 15) - 2;
             } else {
-                int r[9], cc[9];
-                uint32_t cost[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    r[k] = clampi(mr + LR[k], 0, rmax);
-                    cc[k] = clampi(mc + LC[k], 0, cmax);
-                }
-                e.template eval<9>(r, cc, cost);
-                uint32_t best = kInfCost;
-                int best_r = mr, best_c = mc;
-#pragma unroll
-                for (int k = 0; k < 9; k++)
-                    if (cost[k] < best) { best = cost[k]; best_r = r[k]; best_c = cc[k]; }
-                if (best_r == mr && best_c == mc) { last_fast = false; break; }
-                mr = best_r;
-                mc = best_c;
+                if (ldsp_step_clamped(e, rmax, cmax, mr, mc)) { last_fast = false; break; }
             }
         }
         int out_r, out_c;
@@ -887,20 +850,7 @@ __global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant
             out_r = mr + (int)((SRP >> (4 * ks)) & 15) - 2;
             out_c = mc + (int)((SCP >> (4 * ks)) & 15) - 2;
         } else {
-            int r[5], cc[5];
-            uint32_t cost[5];
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                r[k] = clampi(mr + SR[k], 0, rmax);
-                cc[k] = clampi(mc + SC[k], 0, cmax);
-            }
-            e.template eval<5>(r, cc, cost);
-            uint32_t best = kInfCost;
-            out_r = mr;
-            out_c = mc;
-#pragma unroll
-            for (int k = 0; k < 5; k++)
-                if (cost[k] < best) { best = cost[k]; out_r = r[k]; out_c = cc[k]; }
+            sdsp_clamped(e, rmax, cmax, mr, mc, out_r, out_c);
         }
         const int o0 = out_c - bc, o1 = out_r - br;              // bbme.py:531-532
         *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(o0, o1);
