@@ -340,14 +340,13 @@ def main():
     del seq
     prev, cur = planes.view(0, pairs), planes.view(DISTANCE, nf)
     pipe = D.Pipeline(pairs, H, W, dev)
-    dev_out = torch.empty((pairs, 8), dtype=torch.float64, device=dev)
+    dev_out = torch.empty((pairs, 7), dtype=torch.float64, device=dev)
     flush = None if "inputs larger" in config["l2_policy"] else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     total_pairs = pairs * world
 
-    def rows():
+    def rows():                                           # [pairs, 7]: 6 affine parameters + squared-error sum (-> PSNR)
         dev_out[:, :6] = pipe.params
-        dev_out[:, 6] = pipe.sse.to(torch.float64)
-        dev_out[:, 7] = pipe.status.to(torch.float64)
+        dev_out[:, 6] = pipe.sse
         return dev_out
 
     runner = D.HostSequenceRunner(nf, H, W, DISTANCE, chunk=max(1, -(-pairs // max(1, args.e2e_chunks))), procedure=procedure, window=window,
@@ -364,7 +363,7 @@ def main():
             return out
         pipe.run(prev, cur, procedure, window)          # results: pipe.params / pipe.sse / pipe.status / pipe.comp (device)
         if world > 1:                                   # the only exchange of the path: [pairs, 7] rows to every rank
-            GD.gather_rows(rows()[:, :7], total_pairs)
+            GD.gather_rows(rows(), total_pairs)
 
     def barrier():
         if world > 1:
