@@ -72,6 +72,9 @@ def test_bbme_random_geometries(D, golden):
     (250, 333, 8, 5, 0, 0), (250, 333, 8, 5, 3, 0), (250, 333, 4, 3, 1, 1), (250, 333, 4, 6, 2, 0),
     (120, 180, 16, 32, 0, 1),          # window larger than the frame in places
     (100, 100, 20, 4, 0, 0), (100, 100, 20, 4, 3, 0), (100, 100, 7, 3, 1, 0), (64, 96, 5, 9, 2, 0),
+    (200, 260, 16, 60, 0, 1),          # window copies exceed the shared-memory budget: first-generation tiled kernel
+    (64, 300, 8, 130, 0, 0),           # more than 256 row offsets: key packing of the second kernel does not apply
+    (48, 64, 4, 6, 0, 1), (40, 52, 2, 5, 0, 0),      # block sizes 4 and 2: first-generation tiled kernel
 ])
 def test_bbme_vs_oracle(D, H, W, bs, sw, sp, pn):
     seq = S.zoom_rotate_sequence(2, H, W, zoom_per_frame=0.01, deg_per_frame=0.6, seed=H + bs + sp)
