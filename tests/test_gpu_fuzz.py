@@ -56,6 +56,29 @@ def test_bbme_fuzz(D, seed):
             np.testing.assert_array_equal(got, want, err_msg=f"H={H} W={W} bs={bs} sw={sw} sp={sp} pn={pn}")
 
 
+def _near_half(p, R, C, eps):
+    ii, jj = np.mgrid[0:R, 0:C]
+    return any(np.abs(a - np.floor(a) - 0.5).min() < eps
+               for a in (p[0] + p[1] * ii + p[2] * jj, p[3] + p[4] * ii + p[5] * jj))
+
+
+def _rounding_tie(inter, final=None, final_shape=None, eps=1e-9):
+    """True when some model vector a0 + a1*i + a2*j of level 1 or 2 lies within eps of a half-integer: Python's round()
+    then depends on the last bits of the previous level's parameters, which differ between any two float64
+    implementations of the fit (NumPy/BLAS builds included)."""
+    prev = np.asarray(inter[0]["first"], dtype=np.float64)
+    for level in (1, 2):
+        p = prev.copy()
+        p[0] *= 2
+        p[3] *= 2
+        R, C = inter[level]["gt"].shape[:2]
+        if _near_half(p, R, C, eps):
+            return True
+        prev = np.asarray(inter[level]["params"], dtype=np.float64)
+    # ... and the model field of the FINAL parameters, which steers the compensation (results.py:52-54)
+    return final is not None and _near_half(np.asarray(final, dtype=np.float64), final_shape[0], final_shape[1], eps)
+
+
 @pytest.mark.parametrize("seed", range(6 * SCALE))
 def test_pipeline_fuzz(D, seed):
     rng = np.random.default_rng(2000 + seed)
@@ -70,6 +93,8 @@ def test_pipeline_fuzz(D, seed):
         want, inter = O.global_motion_estimation(seq[k], seq[k + d], procedure=sp, window=sw, return_intermediates=True)
         np.testing.assert_array_equal(pipe.intermediate(0)[k].cpu().numpy(), inter[0]["dense"])
         np.testing.assert_array_equal(pipe.intermediate(2)[k].cpu().numpy(), inter[2]["gt"])
+        if _rounding_tie(inter, want, (H // 16, W // 16)):
+            continue      # a model vector sits on a .5 tie: float64 round-off decides it, in the reference too
         np.testing.assert_array_equal(pipe.intermediate(4)[k].cpu().numpy().astype(bool), inter[2]["outlier"])
         np.testing.assert_allclose(pipe.params[k].cpu().numpy(), want, **PARAM_TOL)
         comp = O.compensate_frame(seq[k], O.get_motion_field_affine((H // 16, W // 16), want))
