@@ -367,7 +367,7 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     constexpr int WPR = BS / 4, SPLIT = BS >= 16 ? 2 : 1;
     const int ncand = 2 * a.sw + BS;
     *handled = false;
-    if (ncand > 256 || getenv("GME_EXH_OLD")) return GME_OK;     // key packs the row index in 8 bits
+    if (ncand > 256) return GME_OK;                              // key packs the row index in 8 bits
     Exhaustive2Geom g;
     g.tpb = min(ncand, 384 / SPLIT);
     const int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
@@ -416,12 +416,20 @@ __global__ void __launch_bounds__(256) bbme_exhaustive_generic_kernel(Exhaustive
         const int top = br + j - a.sw, left = bc + ci - a.sw;
         if (top < 0 || left < 0 || top + bs > a.H || left + bs > a.W) continue;
         const uint8_t *cand = cur_plane + (size_t)top * a.pitch + left;
-        uint32_t acc = 0;
-        for (int r = 0; r < bs; r++)
-            for (int c = 0; c < bs; c++) {
+        // exact sum over the row-major pixels [start, start + len) of the block
+        auto range_sum = [&](int start, int len) -> uint32_t {
+            uint32_t sum = 0;
+            int r = start / bs, c = start - r * bs;
+            for (int p = 0; p < len; p++) {
                 const int d = (int)anchor[(size_t)r * a.pitch + c] - (int)cand[(size_t)r * a.pitch + c];
-                acc += (PNORM == GME_PNORM_MAE) ? (uint32_t)abs(d) : (uint32_t)(d * d);
+                sum += (PNORM == GME_PNORM_MAE) ? (uint32_t)abs(d) : (uint32_t)(d * d);
+                if (++c == bs) { c = 0; ++r; }
             }
+            return sum;
+        };
+        // MSE beyond block size 16: the reference's float32 pairwise sum rounds (gme_common.cuh)
+        const uint32_t acc = (PNORM == GME_PNORM_MSE && bs > 16) ? pairwise_sum_f32_tree(bs * bs, range_sum)
+                                                                  : range_sum(0, bs * bs);
         const unsigned long long key = ((unsigned long long)acc << 32) | (unsigned long long)idx;
         best_key = key < best_key ? key : best_key;
     }

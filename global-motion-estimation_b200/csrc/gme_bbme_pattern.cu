@@ -13,7 +13,7 @@
 // Scan orders, strict '<' first-minimum tie-breaking, the diamond clamp to H-bs-1, the
 // swapped SDSP offsets, the double-counted three-step offset and the unbounded 2D-log walk
 // are reproduced exactly; the oracle is oracle/gme_oracle.c.
-#include <cstdlib>
+#include <cstring>
 
 #include "gme_common.cuh"
 
@@ -66,10 +66,14 @@ struct BlockEval {
             if (u < UNITS) {
                 const int ur = u / WPR, uw = u % WPR;
                 const uint8_t *p = prev_plane + (size_t)(br + ur) * pitch + bc + 4 * uw;
-                const int nv = min(4, BS - 4 * uw);
+                if constexpr (BS % 4 == 0) {
+                    v = __ldg(reinterpret_cast<const uint32_t *>(p));   // planes and pitch are 4-byte aligned (checked on the host)
+                } else {
+                    const int nv = min(4, BS - 4 * uw);
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (k < nv) v |= (uint32_t)p[k] << (8 * k);
+                    for (int k = 0; k < 4; k++)
+                        if (k < nv) v |= (uint32_t)p[k] << (8 * k);
+                }
             }
             anchor[t] = v;
         }
@@ -468,273 +472,224 @@ __global__ void __launch_bounds__(NT, 3) bbme_pattern_kernel(const __grid_consta
 
 // ---------------------------------------------------------------------------------------
 // Diamond search on 16 x 16 macroblocks -- the search the GME pipeline runs on L1 and L2
-// (motion.py:224-229), i.e. the dominant kernel of the whole path.
+// (motion.py:224-229), i.e. the dominant kernel of the whole path.  One warp per macroblock;
+// every candidate is scored straight from the staged window by all 32 lanes.  (The first
+// generation kept the 20 x 20 neighbourhood of the centre in registers, one row per lane:
+// 20 of 32 lanes busy, 16 of them useful per candidate, ALU-pipe bound; round 1, profiles/r01k.)
 //
-// One warp per macroblock.  The nine LDSP candidates of a step all lie in the 20 x 20 pixel
-// neighbourhood of the current centre, so that neighbourhood is loaded from the staged window
-// ONCE per step into registers (lane R < 20 owns its row R: two LDS.128 + one LDS.32,
-// byte-aligned with funnel shifts) instead of once per candidate; lane R scores its row against
-// the anchor rows R-2-dr it holds in registers (five rows, loaded once per macroblock) and a
-// candidate's cost is one REDUX.SUM over the warp.  Everything that steers the walk (alignment,
-// costs, the chosen direction) is warp-uniform, so the control flow never diverges.
-// A step re-evaluates only the candidates the previous step has not already scored: the cost
-// of a position does not depend on the step that asks for it, so reusing it is exact, and the
-// strict-'<' scan over the nine costs in the reference's order keeps the tie-breaking.
-// The final SDSP reuses the registers of the last LDSP step (same centre).  Whenever the
-// clamp of bbme.py:503-504 could act (centre within 2 pixels of its bounds) or the
-// neighbourhood leaves the staged window, the step falls back to the candidate-at-a-time
-// evaluator above (BlockEval<16, 32>), which handles clamped and far-away positions.
+// Lane l owns two 4-pixel units of the macroblock: word (l & 3) of rows (l >> 2) and
+// (l >> 2) + 8.  Its two anchor words stay in registers for the whole walk; a candidate is
+// 2 x (two aligned LDS.32 + one funnel shift + VABSDIFF4 + IDP.4A) and one REDUX.SUM -- no
+// masks, no idle lanes, no neighbourhood registers.  The window pitch is 240 bytes
+// (60 words = 28 mod 32), so the eight rows x four words one warp-wide load touches fall
+// into 32 different banks.  The step body is specialised on the direction of the previous
+// move (nine classes of static code, 9 KB in all: a first version that was also specialised
+// on the byte alignment of the centre column, 58 KB, ran out of the 32 KB instruction cache
+// and stalled on fetches, profiles/r02b): the row offsets are immediates, the word address
+// and shift of a column offset are computed once per step, and a step scores only the
+// positions the previous step has not scored (the
+// cost of a position does not depend on the step that asks for it, so reuse is exact; the
+// strict-'<' scan over the nine costs in the reference's order keeps the tie-breaking).
+// Centres within 2 pixels of the clamp bounds of bbme.py:503-504, or whose candidates
+// leave the staged window, take the candidate-at-a-time evaluator (BlockEval<16, 32>, the
+// same lane mapping and anchor registers), which clamps and reads global memory.
 // ---------------------------------------------------------------------------------------
+constexpr int kD16Pitch = 240;                         // window row pitch, bytes (TMA box width)
+constexpr int kD16Rows = 128;                          // window rows: 4 macroblock rows + 2 x 32 margin
+constexpr int kD16Margin = 32;
+
+__host__ __device__ constexpr int ldsp_r(int k)
+{
+    constexpr int t[9] = {0, 2, 1, 0, -1, -2, -1, 0, 1};          // bbme.py:463-472 (row offsets)
+    return t[k];
+}
+__host__ __device__ constexpr int ldsp_c(int k)
+{
+    constexpr int t[9] = {0, 0, 1, 2, 1, 0, -1, -2, -1};
+    return t[k];
+}
+// The centre moved by LDSP offset kb: candidate j of the new step is the position candidate ldsp_reuse(kb, j) of the
+// previous step had (-1: not scored yet).  kb = 0: no previous step.
+__host__ __device__ constexpr int ldsp_reuse(int kb, int j)
+{
+    if (kb == 0) return -1;
+    const int r = ldsp_r(kb) + ldsp_r(j), c = ldsp_c(kb) + ldsp_c(j);
+    for (int i = 0; i < 9; i++)
+        if (ldsp_r(i) == r && ldsp_c(i) == c) return i;
+    return -1;
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// 16 x cost of the candidate (DR, DC) pixels away from the centre.  `xb`: shared BYTE address of this lane's first unit
+// for the centre candidate (any alignment; warp-uniform modulo 4): the unit is read as two aligned words and
+// funnel-shifted into place -- the word address and the shift depend on DC only, so candidates of one step share them.
+// The scale (cost << 4) leaves room for the candidate index of the first-minimum key.
+template <int PNORM, int DR, int DC>
+__device__ __forceinline__ uint32_t d16_cand(uint32_t xb, uint32_t a0, uint32_t a1)
+{
+    const uint32_t A = xb + (uint32_t)DC;
+    const uint32_t addr = (A & ~3u) + (uint32_t)(DR * kD16Pitch);
+    const uint32_t sh = A << 3;                                    // the funnel shift uses the low five bits: (A % 4) * 8
+    const uint32_t u0 = lds_u32(addr), u1 = lds_u32(addr + 4);
+    const uint32_t u2 = lds_u32(addr + 8 * kD16Pitch), u3 = lds_u32(addr + 8 * kD16Pitch + 4);
+    uint32_t acc = cost4_acc<PNORM>(__funnelshift_r(u0, u1, sh), a0, 0u);
+    acc = cost4_acc<PNORM>(__funnelshift_r(u2, u3, sh), a1, acc);
+    return __reduce_add_sync(0xFFFFFFFFu, acc) << 4;
+}
+
+template <int PNORM, int KB, int J>
+__device__ __forceinline__ uint32_t d16_next(const uint32_t (&c)[9], uint32_t xb, uint32_t a0, uint32_t a1)
+{
+    constexpr int i = ldsp_reuse(KB, J);
+    if constexpr (i >= 0)
+        return c[i];
+    else
+        return d16_cand<PNORM, ldsp_r(J), ldsp_c(J)>(xb, a0, a1);
+}
+
+struct D16Fast {          // centres for which the immediate-offset path applies (see the kernel)
+    int r_lo, r_hi, c_lo, c_hi;
+    __device__ __forceinline__ bool ok(int r, int c) const { return r >= r_lo && r <= r_hi && c >= c_lo && c <= c_hi; }
+};
+
+// One LDSP step (bbme.py:494-513) after the move KB (1..8): the centre, its shared address and the costs already
+// known move with static offsets; false (nothing evaluated, c[] stale) when the new centre is not a fast-path one.
+template <int PNORM, int KB>
+__device__ __forceinline__ bool d16_update(uint32_t (&c)[9], int &mr, int &mc, uint32_t &xb, const D16Fast &f,
+                                           uint32_t a0, uint32_t a1)
+{
+    if constexpr (KB != 0) {
+        mr += ldsp_r(KB);
+        mc += ldsp_c(KB);
+        if (!f.ok(mr, mc)) return false;
+        xb += (uint32_t)(ldsp_r(KB) * kD16Pitch + ldsp_c(KB));
+    }
+    const uint32_t n0 = d16_next<PNORM, KB, 0>(c, xb, a0, a1), n1 = d16_next<PNORM, KB, 1>(c, xb, a0, a1),
+                   n2 = d16_next<PNORM, KB, 2>(c, xb, a0, a1), n3 = d16_next<PNORM, KB, 3>(c, xb, a0, a1),
+                   n4 = d16_next<PNORM, KB, 4>(c, xb, a0, a1), n5 = d16_next<PNORM, KB, 5>(c, xb, a0, a1),
+                   n6 = d16_next<PNORM, KB, 6>(c, xb, a0, a1), n7 = d16_next<PNORM, KB, 7>(c, xb, a0, a1),
+                   n8 = d16_next<PNORM, KB, 8>(c, xb, a0, a1);
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3; c[4] = n4; c[5] = n5; c[6] = n6; c[7] = n7; c[8] = n8;
+    return true;
+}
+
+template <int PNORM>
+__device__ __forceinline__ bool d16_ldsp(uint32_t (&c)[9], int kb, int &mr, int &mc, uint32_t &xb, const D16Fast &f,
+                                         uint32_t a0, uint32_t a1)
+{
+    switch (kb) {
+    case 1: return d16_update<PNORM, 1>(c, mr, mc, xb, f, a0, a1);
+    case 2: return d16_update<PNORM, 2>(c, mr, mc, xb, f, a0, a1);
+    case 3: return d16_update<PNORM, 3>(c, mr, mc, xb, f, a0, a1);
+    case 4: return d16_update<PNORM, 4>(c, mr, mc, xb, f, a0, a1);
+    case 5: return d16_update<PNORM, 5>(c, mr, mc, xb, f, a0, a1);
+    case 6: return d16_update<PNORM, 6>(c, mr, mc, xb, f, a0, a1);
+    case 7: return d16_update<PNORM, 7>(c, mr, mc, xb, f, a0, a1);
+    default: return d16_update<PNORM, 8>(c, mr, mc, xb, f, a0, a1);
+    }
+}
+
+// the final SDSP (bbme.py:515-529) around the same centre: key of the first strict minimum, 16 * cost + index, over
+// the effective (row, col) order (0,0) (0,1) (1,0) (0,-1) (-1,0) -- the reference applies its offset list swapped
+template <int PNORM>
+__device__ __forceinline__ uint32_t d16_sdsp(uint32_t centre_cost16, uint32_t xb, uint32_t a0, uint32_t a1)
+{
+    uint32_t key = centre_cost16;
+    key = min(key, d16_cand<PNORM, 0, 1>(xb, a0, a1) + 1u);
+    key = min(key, d16_cand<PNORM, 1, 0>(xb, a0, a1) + 2u);
+    key = min(key, d16_cand<PNORM, 0, -1>(xb, a0, a1) + 3u);
+    key = min(key, d16_cand<PNORM, -1, 0>(xb, a0, a1) + 4u);
+    return key;
+}
+
 template <int PNORM, int NT>
-__global__ void __launch_bounds__(NT, 3) bbme_diamond16_kernel(const __grid_constant__ CUtensorMap cur_map,
-                                                                      const __grid_constant__ CUtensorMap prev_map, PatternArgs a)
+__global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
 {
     constexpr int BS = 16;
+    constexpr int TBX = 8, TBY = 4;                   // macroblocks per tile (fixed: index math by shifts)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ int next_block;                        // walks differ in length: warps take macroblocks from a queue
     if (threadIdx.x == 0) next_block = NT / 32;       // (the first NT/32 are handed out statically)
 
     const int plane = blockIdx.z;
-    constexpr int TBX = 8, TBY = 4;                   // macroblocks per tile (fixed: index math by shifts)
     const int tile_r = blockIdx.y * TBY, tile_c = blockIdx.x * TBX;
-    const int wr0 = tile_r * BS - a.margin, wc0 = (tile_c * BS - a.margin) & ~15;
+    const int wr0 = tile_r * BS - kD16Margin, wc0 = (tile_c * BS - kD16Margin) & ~15;
     const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
     const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
 
-    // the tile's anchor blocks (128 x 64 pixels of `previous`) are staged too, 144 bytes per row so that the
-    // 128-bit row loads of consecutive lanes fall into different banks
-    constexpr int APITCH = 144;
-    uint8_t *anchors = smem + (((size_t)a.win_w * a.win_h + 64 + 127) & ~(size_t)127);
-    if (a.use_tma) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&bar, (uint32_t)(a.win_w * a.win_h + APITCH * TBY * BS));
-            tma_load_3d(smem, &cur_map, &bar, wc0, wr0, plane);
-            tma_load_3d(anchors, &prev_map, &bar, tile_c * BS, tile_r * BS, plane);
-        }
-        mbar_wait(&bar, 0);
-    } else {
-        stage_window(smem, &bar, &cur_map, 0, cur_plane, plane, a.H, a.W, a.pitch, wr0, wc0, a.win_w, a.win_h);
-        for (int i = threadIdx.x; i < TBY * BS * (TBX * BS / 4); i += NT) {
-            const int r = i / (TBX * BS / 4), w = i % (TBX * BS / 4);
-            const int rr = tile_r * BS + r, cc = tile_c * BS + 4 * w;
-            uint32_t v = 0;
-            if (rr < a.H) {
-                const uint8_t *p = prev_plane + (size_t)rr * a.pitch;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (cc + k < a.W) v |= (uint32_t)p[cc + k] << (8 * k);
-            }
-            *reinterpret_cast<uint32_t *>(anchors + r * APITCH + 4 * w) = v;
-        }
-        __syncthreads();
-    }
+    stage_window(smem, &bar, &cur_map, a.use_tma, cur_plane, plane, a.H, a.W, a.pitch, wr0, wc0, kD16Pitch, kD16Rows);
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);   // tells the compiler it is warp-uniform
-    BlockEval<BS, 32, PNORM> e;                       // fallback evaluator: 32 lanes share one candidate
+    BlockEval<BS, 32, PNORM> e;                       // border / far-away evaluator; owns the anchor registers
     e.cur_plane = cur_plane;
     e.win = reinterpret_cast<const uint32_t *>(smem);
     e.pitch = a.pitch;
-    e.win_pw = a.win_w / 4;
+    e.win_pw = kD16Pitch / 4;
     e.wr0 = wr0;
     e.wc0 = wc0;
-    e.wr1 = wr0 + a.win_h;
-    e.wc1 = wc0 + a.win_w - 4;
+    e.wr1 = wr0 + kD16Rows;
+    e.wc1 = wc0 + kD16Pitch - 4;
     e.lane_g = lane;
     e.gmask = 0xFFFFFFFFu;
 
-    // the LDSP / SDSP offset tables of ldsp_step_clamped / sdsp_clamped, packed for lookups by a run-time index
-    // without a local-memory array (3 bits per entry, value + 2, entry k at bit 3k)
-    constexpr unsigned LRP = 2u | (4u << 3) | (3u << 6) | (2u << 9) | (1u << 12) | (0u << 15) | (1u << 18) | (2u << 21) | (3u << 24);
-    constexpr unsigned LCP = 2u | (2u << 3) | (3u << 6) | (4u << 9) | (3u << 12) | (2u << 15) | (1u << 18) | (0u << 21) | (1u << 24);
     constexpr unsigned SRP = 2u | (2u << 3) | (3u << 6) | (2u << 9) | (1u << 12);
     constexpr unsigned SCP = 2u | (3u << 3) | (2u << 6) | (1u << 9) | (2u << 12);
     const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
-    // centres for which the register path applies: no clamp can act on the 5 x 5 neighbourhood of offsets, and the
-    // 20 x 20 pixel neighbourhood (read as 6 aligned words) lies inside the staged window
-    const int fr_lo = max(2, wr0 + 2), fr_hi = min(rmax - 2, wr0 + a.win_h - 18);
-    const int fc_lo = max(2, wc0 + 2), fc_hi = min(cmax - 2, wc0 + 2 + a.win_w - 24);
-    const int Rl = min(lane, 19);                              // neighbourhood row this lane loads
-    const uint32_t row_base = smem_u32(smem) + (uint32_t)(Rl * a.win_w);
+    // centres for which the immediate-offset path applies: no clamp can act on the 5 x 5 neighbourhood of offsets, and
+    // every word a candidate reads (16 + 2 rows, 16 + 2 columns + the word the funnel shift completes) is staged
+    D16Fast fast;
+    fast.r_lo = max(2, wr0 + 2); fast.r_hi = min(rmax - 2, wr0 + kD16Rows - BS - 2);
+    fast.c_lo = max(2, wc0 + 2); fast.c_hi = min(cmax - 2, wc0 + kD16Pitch - BS - 2 - 7);
+    // this lane's first unit: row lane / 4, word lane % 4 (the second is eight rows below)
+    const uint32_t lane_base = smem_u32(smem) + (uint32_t)((lane >> 2) * kD16Pitch + (lane & 3) * 4);
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
 
     for (int b = warp; b < TBX * TBY; b = __shfl_sync(0xFFFFFFFFu, lane == 0 ? atomicAdd(&next_block, 1) : 0, 0)) {
         const int bi = tile_r + b / TBX, bj = tile_c + b % TBX;
         if (bi >= a.R || bj >= a.C) continue;
         const int br = bi * BS, bc = bj * BS;
-        const uint8_t *anchor0 = anchors + (b / TBX) * BS * APITCH + (b % TBX) * BS;   // top-left pixel of the anchor block
-
-        // anchor rows for the register path: anc[d] = anchor row lane - d, scored when a candidate has dr = d - 2;
-        // msk[d] zeroes the contribution of lanes whose row lies outside that candidate
-        // (the rows themselves stay in shared memory and are re-read per candidate with one LDS.128: twenty fewer
-        // live registers keep the loop-invariant values of the walk in registers at three CTAs per SM.  Lanes whose
-        // row lies outside a candidate read some in-bounds row -- the tile is padded -- and are masked.)
-        uint32_t msk[5];
-#pragma unroll
-        for (int d = 0; d < 5; d++) {
-            const int k = lane - d;
-            msk[d] = (lane < 20 && k >= 0 && k < BS) ? 1u : 0u;
-        }
-        const uint32_t anc_addr = smem_u32(anchor0) + (uint32_t)(lane * APITCH);      // anchor row `lane`; row lane - d is d rows up
-
-        uint32_t z[5] = {0, 0, 0, 0, 0};   // bytes 0..19 of this lane's neighbourhood row; byte 0 = image column mc - 2
-        auto load_region = [&](int mr, int mc) {
-            // six aligned words that cover bytes xs .. xs+19 of this lane's row, read at a run-time word address
-            // (32-bit shared address kept in a register: no generic-address arithmetic in the loop)
-            const int xs = mc - 2 - wc0;
-            const uint32_t addr = row_base + (uint32_t)((mr - 2 - wr0) * a.win_w + (xs & ~3));
-            uint32_t u[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u[i]) : "r"(addr + 4 * i));
-            const int bsh = (xs & 3) * 8;
-#pragma unroll
-            for (int i = 0; i < 5; i++) z[i] = __funnelshift_r(u[i], u[i + 1], bsh);
-        };
-        // cost of the candidate at column offset dc (the shifted words s) and row offset dr = d - 2
-        auto cand = [&](const uint32_t (&s)[4], int d) -> uint32_t {
-            uint32_t an[4];
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(an[0]), "=r"(an[1]), "=r"(an[2]), "=r"(an[3]) : "r"(anc_addr - (uint32_t)(d * APITCH)));
-            uint32_t acc = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) acc = cost4_acc<PNORM>(s[i], an[i], acc);
-            return __reduce_add_sync(0xFFFFFFFFu, acc * msk[d]);     // msk: 0 / 1 (IMAD: the FMA pipe has room, the ALU pipe does not)
-        };
-        auto shifted = [&](int bits, uint32_t (&s)[4]) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) s[i] = __funnelshift_r(z[i], z[i + 1], bits);
-        };
+        e.load_anchor(prev_plane, br, bc);
+        const uint32_t a0 = e.anchor[0], a1 = e.anchor[1];
 
         int mr = br, mc = bc;
-        uint32_t c[9];
-        bool have = false, last_fast = false;     // have: c[] are the costs around the previous centre, which moved by L[kb]
-        int kb = 0;
+        uint32_t c[9];                                             // 16 x cost of the nine LDSP positions around (mr, mc)
+        int kb = 0;                                                // the move that leads to the next centre; 0: c[] holds nothing
+        bool last_fast = false;
+        uint32_t xb = 0;
         for (;;) {                                                 // LDSP, bbme.py:494-513
-            if (mr >= fr_lo && mr <= fr_hi && mc >= fc_lo && mc <= fc_hi) {
-                load_region(mr, mc);
-                if (!have) {
-                    uint32_t s[4];
-                    shifted(16, s);
-                    c[0] = cand(s, 2); c[1] = cand(s, 4); c[5] = cand(s, 0);
-                    shifted(24, s);
-                    c[2] = cand(s, 3); c[4] = cand(s, 1);
-                    shifted(8, s);
-                    c[6] = cand(s, 1); c[8] = cand(s, 3);
-                    { const uint32_t t[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(t, 2); }
-                    { const uint32_t t[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(t, 2); }
-                } else {
-                    // only the candidates the previous step has not scored; the others keep their cost (exact: the
-                    // cost of a position does not depend on which step asks for it)
-                    switch (kb) {
-                    case 1: {                                       // centre moved by (2, 0)
-                        const uint32_t n0 = c[1]; const uint32_t n4 = c[2]; const uint32_t n5 = c[0]; const uint32_t n6 = c[8];
-                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
-                        { uint32_t s[4]; shifted(8, s); c[8] = cand(s, 3); }
-                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); }
-                        { uint32_t s[4]; shifted(24, s); c[2] = cand(s, 3); }
-                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
-                        c[0] = n0; c[4] = n4; c[5] = n5; c[6] = n6;
-                        break;
-                    }
-                            case 2: {                                       // centre moved by (1, 1)
-                        const uint32_t n0 = c[2]; const uint32_t n4 = c[3]; const uint32_t n5 = c[4]; const uint32_t n6 = c[0]; const uint32_t n7 = c[8]; const uint32_t n8 = c[1];
-                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); }
-                        { uint32_t s[4]; shifted(24, s); c[2] = cand(s, 3); }
-                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
-                        c[0] = n0; c[4] = n4; c[5] = n5; c[6] = n6; c[7] = n7; c[8] = n8;
-                        break;
-                    }
-                            case 3: {                                       // centre moved by (0, 2)
-                        const uint32_t n0 = c[3]; const uint32_t n6 = c[4]; const uint32_t n7 = c[0]; const uint32_t n8 = c[2];
-                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); c[5] = cand(s, 0); }
-                        { uint32_t s[4]; shifted(24, s); c[2] = cand(s, 3); c[4] = cand(s, 1); }
-                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
-                        c[0] = n0; c[6] = n6; c[7] = n7; c[8] = n8;
-                        break;
-                    }
-                            case 4: {                                       // centre moved by (-1, 1)
-                        const uint32_t n0 = c[4]; const uint32_t n1 = c[2]; const uint32_t n2 = c[3]; const uint32_t n6 = c[5]; const uint32_t n7 = c[6]; const uint32_t n8 = c[0];
-                        { uint32_t s[4]; shifted(16, s); c[5] = cand(s, 0); }
-                        { uint32_t s[4]; shifted(24, s); c[4] = cand(s, 1); }
-                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
-                        c[0] = n0; c[1] = n1; c[2] = n2; c[6] = n6; c[7] = n7; c[8] = n8;
-                        break;
-                    }
-                            case 5: {                                       // centre moved by (-2, 0)
-                        const uint32_t n0 = c[5]; const uint32_t n1 = c[0]; const uint32_t n2 = c[4]; const uint32_t n8 = c[6];
-                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
-                        { uint32_t s[4]; shifted(8, s); c[6] = cand(s, 1); }
-                        { uint32_t s[4]; shifted(16, s); c[5] = cand(s, 0); }
-                        { uint32_t s[4]; shifted(24, s); c[4] = cand(s, 1); }
-                        { const uint32_t s[4] = {z[1], z[2], z[3], z[4]}; c[3] = cand(s, 2); }
-                        c[0] = n0; c[1] = n1; c[2] = n2; c[8] = n8;
-                        break;
-                    }
-                            case 6: {                                       // centre moved by (-1, -1)
-                        const uint32_t n0 = c[6]; const uint32_t n1 = c[8]; const uint32_t n2 = c[0]; const uint32_t n3 = c[4]; const uint32_t n4 = c[5]; const uint32_t n8 = c[7];
-                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
-                        { uint32_t s[4]; shifted(8, s); c[6] = cand(s, 1); }
-                        { uint32_t s[4]; shifted(16, s); c[5] = cand(s, 0); }
-                        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3; c[4] = n4; c[8] = n8;
-                        break;
-                    }
-                            case 7: {                                       // centre moved by (0, -2)
-                        const uint32_t n0 = c[7]; const uint32_t n2 = c[8]; const uint32_t n3 = c[0]; const uint32_t n4 = c[6];
-                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
-                        { uint32_t s[4]; shifted(8, s); c[6] = cand(s, 1); c[8] = cand(s, 3); }
-                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); c[5] = cand(s, 0); }
-                        c[0] = n0; c[2] = n2; c[3] = n3; c[4] = n4;
-                        break;
-                    }
-                            case 8: {                                       // centre moved by (1, -1)
-                        const uint32_t n0 = c[8]; const uint32_t n2 = c[1]; const uint32_t n3 = c[2]; const uint32_t n4 = c[0]; const uint32_t n5 = c[6]; const uint32_t n6 = c[7];
-                        { const uint32_t s[4] = {z[0], z[1], z[2], z[3]}; c[7] = cand(s, 2); }
-                        { uint32_t s[4]; shifted(8, s); c[8] = cand(s, 3); }
-                        { uint32_t s[4]; shifted(16, s); c[1] = cand(s, 4); }
-                        c[0] = n0; c[2] = n2; c[3] = n3; c[4] = n4; c[5] = n5; c[6] = n6;
-                        break;
-                    }
-                    default: break;
-                    }
+            if (kb == 0) {                                         // (re)start at (mr, mc)
+                if (!fast.ok(mr, mc)) {
+                    if (ldsp_step_clamped(e, rmax, cmax, mr, mc)) { last_fast = false; break; }
+                    continue;
                 }
-                // first strict minimum in candidate order (bbme.py:506-510): costs < 2^24, so (cost, index) packs in 32 bits
-                uint32_t key = c[0] << 4;
-#pragma unroll
-                for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
-                kb = (int)(key & 15u);
-                if (kb == 0) { last_fast = true; break; }          // the centre wins: positions are distinct here
-                mr += (int)((LRP >> (3 * kb)) & 7u) - 2;
-                mc += (int)((LCP >> (3 * kb)) & 7u) - 2;
-                have = true;
-            } else {
-                e.load_anchor(prev_plane, br, bc);
-                have = false;
-                if (ldsp_step_clamped(e, rmax, cmax, mr, mc)) { last_fast = false; break; }
+                xb = lane_base + (uint32_t)((mr - wr0) * kD16Pitch + (mc - wc0));
+                d16_update<PNORM, 0>(c, mr, mc, xb, fast, a0, a1);
+            } else if (!d16_ldsp<PNORM>(c, kb, mr, mc, xb, fast, a0, a1)) {
+                kb = 0;                                            // the move took the centre off the fast path
+                continue;
             }
+            // first strict minimum in candidate order (bbme.py:506-510): costs < 2^24, so 16 * cost + index fits
+            uint32_t key = c[0];
+#pragma unroll
+            for (int j = 1; j < 9; j++) key = min(key, c[j] + (uint32_t)j);
+            kb = (int)(key & 15u);
+            if (kb == 0) { last_fast = true; break; }              // the centre wins: positions are distinct here
         }
 
         int out_r, out_c;
-        if (last_fast) {                                           // SDSP on the registers of the last step
-            uint32_t s0[4], sp[4], sm[4];
-            shifted(16, s0);
-            shifted(24, sp);
-            shifted(8, sm);
-            uint32_t key = c[0] << 4;
-            key = min(key, (cand(sp, 2) << 4) | 1u);               // (0, +1)
-            key = min(key, (cand(s0, 3) << 4) | 2u);               // (+1, 0)
-            key = min(key, (cand(sm, 2) << 4) | 3u);               // (0, -1)
-            key = min(key, (cand(s0, 1) << 4) | 4u);               // (-1, 0)
-            const int ks = (int)(key & 15u);
+        if (last_fast) {                                           // SDSP around the centre of the last step
+            const int ks = (int)(d16_sdsp<PNORM>(c[0], xb, a0, a1) & 15u);
             out_r = mr + (int)((SRP >> (3 * ks)) & 7u) - 2;
             out_c = mc + (int)((SCP >> (3 * ks)) & 7u) - 2;
         } else {
-            e.load_anchor(prev_plane, br, bc);
             sdsp_clamped(e, rmax, cmax, mr, mc, out_r, out_c);
         }
         if (lane == 0)
@@ -885,15 +840,22 @@ struct GenericEval {
 #pragma unroll 1
         for (int k = 0; k < N; k++) {
             const uint8_t *cand = cur_plane + (size_t)r[k] * pitch + c[k];
-            uint32_t acc = 0;
-            for (int p = lane; p < npix; p += 32) {
-                const int pr = p / bs, pc = p - pr * bs;
-                const int d = (int)prev_block[(size_t)pr * pitch + pc] - (int)cand[(size_t)pr * pitch + pc];
-                acc += (PNORM == GME_PNORM_MAE) ? (uint32_t)abs(d) : (uint32_t)(d * d);
-            }
+            // exact warp-wide sum over the row-major pixels [start, start + len) of the block
+            auto range_sum = [&](int start, int len) -> uint32_t {
+                uint32_t acc = 0;
+                for (int p = start + lane; p < start + len; p += 32) {
+                    const int pr = p / bs, pc = p - pr * bs;
+                    const int d = (int)prev_block[(size_t)pr * pitch + pc] - (int)cand[(size_t)pr * pitch + pc];
+                    acc += (PNORM == GME_PNORM_MAE) ? (uint32_t)abs(d) : (uint32_t)(d * d);
+                }
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-            cost[k] = acc;
+                for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                return acc;
+            };
+            if (PNORM == GME_PNORM_MSE && bs > 16)
+                cost[k] = pairwise_sum_f32_tree(npix, range_sum);     // the reference's float32 sum rounds here
+            else
+                cost[k] = range_sum(0, npix);                         // exact in the reference's float32 too
         }
     }
 };
@@ -964,22 +926,15 @@ static int launch_diamond16(PatternArgs a, int n, cudaStream_t stream)
 {
     constexpr int NT = 256, BS = 16;
     const int tbx = 8, tby = 4;                          // fixed in the kernel (TBX, TBY)
-    const int margin = 32;
-    int win_w = tbx * BS + 2 * margin + 4 + 15;          // as launch_fast: funnel slack + 16-byte rounding of column 0
-    win_w = (win_w + 15) / 16 * 16;
-    const int win_h = tby * BS + 2 * margin;
-    a.tbx = tbx; a.tby = tby; a.margin = margin; a.win_w = win_w; a.win_h = win_h;
+    a.tbx = tbx; a.tby = tby; a.margin = kD16Margin; a.win_w = kD16Pitch; a.win_h = kD16Rows;
     CUtensorMap map;
-    CUtensorMap pmap;
-    a.use_tma = (make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h) &&
-                 make_plane_tensor_map(&pmap, a.prev, n, a.H, a.W, a.pitch, a.prev_stride, 144, tby * BS)) ? 1 : 0;
-    if (!a.use_tma) { memset(&map, 0, sizeof(map)); memset(&pmap, 0, sizeof(pmap)); }
-    // window (+64: the register path reads 36 bytes from a 16-byte boundary), then the anchor tile (144 x 64)
-    const size_t smem = (((size_t)win_w * win_h + 64 + 127) & ~(size_t)127) + (size_t)144 * (tby * BS + 32);   // + 32 padding rows
+    a.use_tma = make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, kD16Pitch, kD16Rows) ? 1 : 0;
+    if (!a.use_tma) memset(&map, 0, sizeof(map));
+    const size_t smem = (size_t)kD16Pitch * kD16Rows + 32;   // slack: the border evaluator's funnel shift reads one word past a row
     auto kern = bbme_diamond16_kernel<PNORM, NT>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
-    kern<<<grid, NT, smem, stream>>>(map, pmap, a);
+    kern<<<grid, NT, smem, stream>>>(map, a);
     note_launch();
     return check_launch("bbme_diamond16_kernel");
 }
@@ -1009,10 +964,8 @@ static int launch_diamond2(PatternArgs a, int n, cudaStream_t stream)
 template <int PNORM>
 static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
 {
-    if (bs == 2 && a.procedure == GME_SEARCH_DIAMOND && getenv("GME_DIAMOND2_OLD") == nullptr)
-        return launch_diamond2<PNORM>(a, n, stream);
-    if (bs == 16 && a.procedure == GME_SEARCH_DIAMOND && !a.sums && getenv("GME_DIAMOND16_OLD") == nullptr)
-        return launch_diamond16<PNORM>(a, n, stream);
+    if (bs == 2 && a.procedure == GME_SEARCH_DIAMOND) return launch_diamond2<PNORM>(a, n, stream);
+    if (bs == 16 && a.procedure == GME_SEARCH_DIAMOND && !a.sums) return launch_diamond16<PNORM>(a, n, stream);
     switch (bs) {
     case 2: return launch_fast<2, 1, PNORM>(a, n, stream);
     case 4: return launch_fast<4, 1, PNORM>(a, n, stream);

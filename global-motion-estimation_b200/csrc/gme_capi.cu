@@ -100,8 +100,6 @@ static EncodeTiledFn encode_fn()
 bool make_plane_tensor_map(CUtensorMap *map, const uint8_t *base, int n, int H, int W, size_t pitch,
                            size_t plane_stride, int box_w, int box_h)
 {
-    static const bool disabled = getenv("GME_NO_TMA") != nullptr;   // debugging aid: cooperative loader everywhere
-    if (disabled) return false;
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     if ((reinterpret_cast<uintptr_t>(base) % 16) || (pitch % 16) || (n > 1 && plane_stride % 16)) return false;

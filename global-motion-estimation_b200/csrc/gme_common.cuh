@@ -122,4 +122,42 @@ __device__ __host__ __forceinline__ uint32_t byte_mask(int nvalid)
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// The float32 value np.sum gives for the bs*bs squared differences of one block (compute_dfd + mse, bbme.py:61-64,94)
+// when block_size > 16, i.e. when the exact sum can exceed 2^24 and the reference's float32 arithmetic ROUNDS
+// (SURVEY A.2).  NumPy reduces a contiguous float32 buffer pairwise (numpy/core/src/umath/loops_utils.h.src,
+// pairwise_sum_FLOAT; numpy pinned by requirements.txt:2): runs of at most 128 values are summed with eight strided
+// accumulators -- every partial sum there is an integer below 2^24, hence exact -- and longer runs are split at
+// n/2 rounded down to a multiple of 8, the two halves added in float32.  `leaf(start, len)` returns the exact integer
+// sum of the row-major values [start, start + len); the tree above the leaves is followed with round-to-nearest adds.
+// The result is an integer-valued float below 2^32 (bs <= 255), returned as the integer.  Oracle: pairwise_sum_f32 in
+// oracle/gme_oracle.c; pinned against the reference by tests/golden/bbme_f32_rounding.npz.
+template <class Leaf>
+__device__ __forceinline__ uint32_t pairwise_sum_f32_tree(int n, Leaf leaf)
+{
+    if (n <= 128) return leaf(0, n);
+    int st_start[12], st_len[12], st_state[12];       // depth <= 9 for n <= 255 * 255
+    float st_left[12];
+    int sp = 0;
+    st_start[0] = 0; st_len[0] = n; st_state[0] = 0;
+    float ret = 0.f;
+    while (sp >= 0) {
+        const int s = st_start[sp], l = st_len[sp];
+        if (l <= 128) { ret = (float)leaf(s, l); --sp; continue; }
+        int n2 = l / 2;
+        n2 -= n2 % 8;
+        if (st_state[sp] == 0) {
+            st_state[sp] = 1;
+            ++sp; st_start[sp] = s; st_len[sp] = n2; st_state[sp] = 0;
+        } else if (st_state[sp] == 1) {
+            st_left[sp] = ret;
+            st_state[sp] = 2;
+            ++sp; st_start[sp] = s + n2; st_len[sp] = l - n2; st_state[sp] = 0;
+        } else {
+            ret = __fadd_rn(st_left[sp], ret);
+            --sp;
+        }
+    }
+    return (uint32_t)ret;
+}
+
 }  // namespace gme

@@ -58,8 +58,10 @@ GME_API int gme_last_cuda_error(void);
 
 /* bbme.get_motion_field (bbme.py:12-38) + the four *_search procedures (bbme.py:105-534),
  * batched over n frame pairs.  Anchor blocks come from prev, candidates from cur.
- * Costs are exact integers (SAD / SSD); bit-identical to the reference's float32 sums for
- * MAE with block_size <= 255 and MSE with block_size <= 16.
+ * Costs are exact integers (SAD / SSD), which is what the reference's float32 sums are for
+ * MAE with block_size <= 255 and MSE with block_size <= 16; MSE with a larger
+ * block rounds in the reference (NumPy's pairwise float32 sum) and the kernels reproduce that
+ * rounding node by node, so the fields are bit-identical there too.
  * GME_ERR_UNSUPPORTED: block_size > 255; diamond with H <= bs or W <= bs (bbme.py:503-504
  * clamps to a negative bound there). */
 GME_API int gme_bbme_motion_field(const uint8_t *prev, size_t prev_plane_stride,

@@ -5,6 +5,8 @@ Bars: motion fields, outlier masks, thresholds, model fields, compensated frames
 sums are BIT-EXACT; affine parameters within atol = rtol = 1e-9 (PARAM_TOL; the reference accumulates
 the normal equations in float64 term by term, the kernel sums exact integers and rounds once); PSNR
 within 1e-12 relative."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -55,6 +57,20 @@ def test_bbme_random_geometries(D, golden):
         got = field_of(D, g[f"p{inp}"], g[f"c{inp}"], bs, sw, sp, pn)[0]
         if not np.array_equal(got, g[f"mf{k}"]):
             bad.append((k, bs, sw, sp, pn, int((got != g[f"mf{k}"]).sum())))
+    assert not bad, bad
+
+
+def test_bbme_mse_block_sizes_beyond_16_round_like_float32(D, golden):
+    """128 reference cases with MSE and block sizes 17..40, where the reference's float32 cost exceeds 2^24 and rounds
+    at the nodes of NumPy's pairwise sum: high-contrast inputs, some built so that candidates tie exactly
+    as integers and the rounding decides the winner (an exact-integer argmin gets those blocks wrong)."""
+    g = golden("bbme_f32_rounding")
+    bad = []
+    for k in range(int(g["n"])):
+        bs, sw, sp, pn, inp = (int(v) for v in g[f"a{k}"])
+        got = field_of(D, g[f"p{inp}"], g[f"c{inp}"], bs, sw, sp, pn)[0]
+        if not np.array_equal(got, g[f"mf{k}"]):
+            bad.append((k, bs, sw, sp, int((got != g[f"mf{k}"]).sum())))
     assert not bad, bad
 
 
@@ -339,6 +355,30 @@ def test_pipeline_properties_4k(D):
     same = D.Pipeline(1, H, W)
     same.run(pp, pp)
     assert same.psnr()[0] == -1 or same.psnr()[0].real > 40      # static content: the -1 edge vectors cost little
+
+
+def test_pipeline_config5_full_size(D):
+    """Config 5 AT SIZE: one 2160x3840 general-affine pair (frame distance 3) through gme_pipeline with exhaustive
+    search, sw = 32, on the bs-16 levels, against the threaded oracle: dense field, both exhaustive fields
+    (64.7 G pixel-pair operations), both outlier masks, parameters, compensated frame and squared error."""
+    H, W, d = 2160, 3840, 3
+    seq = S.affine_sequence(d + 1, H, W, seed=5)
+    prev, cur = seq[0], seq[d]
+    pipe = D.Pipeline(1, H, W)
+    pipe.run(D.Planes.from_host(prev), D.Planes.from_host(cur), procedure=0, window=32)
+    torch.cuda.synchronize()
+    assert int(pipe.status.item()) == 0
+    want, inter = O.global_motion_estimation(prev, cur, procedure=0, window=32, return_intermediates=True,
+                                             threads=len(os.sched_getaffinity(0)))
+    np.testing.assert_array_equal(pipe.intermediate(0)[0].cpu().numpy(), inter[0]["dense"])
+    np.testing.assert_array_equal(pipe.intermediate(1)[0].cpu().numpy(), inter[1]["gt"])
+    np.testing.assert_array_equal(pipe.intermediate(2)[0].cpu().numpy(), inter[2]["gt"])
+    np.testing.assert_array_equal(pipe.intermediate(3)[0].cpu().numpy().astype(bool), inter[1]["outlier"])
+    np.testing.assert_array_equal(pipe.intermediate(4)[0].cpu().numpy().astype(bool), inter[2]["outlier"])
+    np.testing.assert_allclose(pipe.params[0].cpu().numpy(), want, **PARAM_TOL)
+    comp = O.compensate_frame(prev, O.get_motion_field_affine((H // 16, W // 16), want))
+    np.testing.assert_array_equal(pipe.comp.to_host()[0], comp)
+    assert int(pipe.sse.item()) == O.sse(cur, comp)
 
 
 # ------------------------------------------------------------------ sequence mode, host runner, stage timing

@@ -48,7 +48,7 @@ def run_case(name):
     elif name == "sse":
         s = D.sse(pp, cp); torch.cuda.synchronize()
         ok = int(s.item()) == O.sse(prev, cur)
-    print(f"CASE {name} tma={'off' if os.environ.get('GME_NO_TMA') else 'on'}: {'OK' if ok else 'MISMATCH'}", flush=True)
+    print(f"CASE {name}: {'OK' if ok else 'MISMATCH'}", flush=True)
 
 
 if __name__ == "__main__":
@@ -56,13 +56,8 @@ if __name__ == "__main__":
         run_case(sys.argv[2])
         sys.exit(0)
     cases = sys.argv[1:] or CASES
-    for tma in ("on", "off"):
-        for c in cases:
-            env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
-            if tma == "off":
-                env["GME_NO_TMA"] = "1"
-            else:
-                env.pop("GME_NO_TMA", None)
-            r = subprocess.run([sys.executable, __file__, "--one", c], env=env, capture_output=True, text=True, timeout=300)
-            tail = (r.stdout + r.stderr).strip().splitlines()[-3:]
-            print(f"[{c} tma={tma}] rc={r.returncode} :: " + " | ".join(tail), flush=True)
+    for c in cases:
+        env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+        r = subprocess.run([sys.executable, __file__, "--one", c], env=env, capture_output=True, text=True, timeout=300)
+        tail = (r.stdout + r.stderr).strip().splitlines()[-3:]
+        print(f"[{c}] rc={r.returncode} :: " + " | ".join(tail), flush=True)
