@@ -172,6 +172,32 @@ def cpu_pairs_per_s(frames: np.ndarray, procedure: int, window: int, n_pairs: in
     return n_pairs / dt, dt
 
 
+def dropin_pairs_per_s(frames, n_pairs: int, reps: int = 1):
+    """The per-pair surface results.py drives (results.py:50-59,109): NumPy frames in, NumPy results out, four calls
+    per pair through the drop-in modules -- motion.global_motion_estimation, motion.get_motion_field_affine,
+    motion.compensate_frame, utils.PSNR.  Host wall clock (every call synchronises).  Returns (pairs/s, seconds)."""
+    import motion
+    import utils
+    H, W = frames[0].shape
+    shape = (int(H / motion.BBME_BLOCK_SIZE), int(W / motion.BBME_BLOCK_SIZE), 2)
+    n_avail = len(frames) - DISTANCE
+
+    def one(k):
+        previous, current = frames[k % n_avail], frames[k % n_avail + DISTANCE]
+        params = motion.global_motion_estimation(previous, current)
+        model = motion.get_motion_field_affine(shape, parameters=params)
+        compensated = motion.compensate_frame(previous, model)
+        return params, utils.PSNR(current, compensated)
+
+    one(0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for k in range(n_pairs):
+            one(k)
+    dt = time.perf_counter() - t0
+    return n_pairs * reps / dt, dt
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -207,9 +233,11 @@ def exhaustive_ops(H, W, bs, sw):
     return rows * cols * bs * bs
 
 
-def bench_exhaustive(D, N, torch, planes, dev):
+def bench_exhaustive(D, N, torch, planes, dev, sm_mhz=1965.0):
     """BBME SAD Gop/s vs the integer-pipe roofline (BASELINE.json metric, second half): the exhaustive kernel on
-    config-1 and config-5 shaped inputs, against the rate of its own instruction mix measured by the probe."""
+    config-1 and config-5 shaped inputs, against (a) the ceiling of the packed-byte pipe, 148 SMs x 64 lanes x 4 pixels
+    x f_SM pixel-pairs/s (one VABSDIFF4 per lane and clock; 74.4 T/s at 1965 MHz), and (b) the rate the search's own
+    instruction mix sustains on registers, measured by the probe kernel (gme_sad_peak_probe)."""
     import ctypes
     out = {}
     scratch = torch.zeros(1024, dtype=torch.int32, device=dev)
@@ -228,6 +256,9 @@ def bench_exhaustive(D, N, torch, planes, dev):
         return a.elapsed_time(b) * 1e-3 / reps
 
     peaks = {}
+    pipe_peak = 148 * 64 * 4 * sm_mhz * 1e6
+    out["pipe_peak_tops"] = pipe_peak / 1e12
+    out["pipe_peak_formula"] = f"148 SMs x 64 lanes x 4 pixels x {sm_mhz:.0f} MHz"
     for pn, name in ((0, "sad"), (1, "ssd")):
         npix = ctypes.c_uint64(0)
         t = timed(lambda: N.check(N.lib.gme_sad_peak_probe(pn, 148 * 16, 2048, scratch.data_ptr(), ctypes.byref(npix), stream)), 5)
@@ -246,7 +277,8 @@ def bench_exhaustive(D, N, torch, planes, dev):
             prev, cur = crop.view(0, n), crop.view(DISTANCE, DISTANCE + n)
         t = timed(lambda: D.motion_field(prev, cur, bs, sw, 0, pn), 5)
         ops = exhaustive_ops(h, w, bs, sw) * n
-        out[name] = {"tops": ops / t / 1e12, "ms": t * 1e3, "pixel_pair_ops": ops, "frac_of_probe_peak": ops / t / peaks[pn]}
+        out[name] = {"tops": ops / t / 1e12, "ms": t * 1e3, "pixel_pair_ops": ops, "frac_of_pipe_peak": ops / t / pipe_peak,
+                     "frac_of_probe_peak": ops / t / peaks[pn]}
     return out
 
 
@@ -264,7 +296,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "dropin"])
     ap.add_argument("--workload", default="gme_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -301,6 +333,8 @@ def main():
             t += dt
         value = per_step * args.steps / t
         sample = f"{per_step} pairs per step drawn cyclically from an {nf}-frame sequence, one pair per thread"
+        config["pairs_per_step_per_gpu"] = per_step        # what this arm ran per step (a bounded sample of the workload)
+        config["l2_policy"] = "n/a (CPU arm)"
         emit({
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
@@ -308,6 +342,31 @@ def main():
             "data": "synthetic", "config": config,
             "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, real_stdout)
+        return
+
+    if args.impl == "dropin":
+        # the reference-facing per-pair surface, the path results.py drives: one frame pair per call, host NumPy in/out
+        if rank != 0:
+            return
+        import torch
+        torch.cuda.set_device(local_rank)
+        n = min(pairs, 32)
+        seq = make_sequence(n + DISTANCE, H, W, motion, seed=4, device=torch.device("cuda", local_rank)).cpu().numpy()
+        frames = [np.ascontiguousarray(f) for f in seq]
+        for _ in range(max(1, args.warmup)):
+            dropin_pairs_per_s(frames, min(n, 4))
+        sampler = ClockSampler(local_rank)
+        with sampler:
+            v, dt = dropin_pairs_per_s(frames, n, reps=max(1, args.steps))
+        config["pairs_per_step_per_gpu"] = n
+        nbytes = 6 * H * W + 48 + (H // 16) * (W // 16) * 8          # frames uploaded by the four calls + parameters + field
+        emit({"impl": "dropin", "metric": metric, "value": v, "unit": unit, "n_gpus": 1, "steps": max(1, args.steps),
+              "warmup": max(1, args.warmup), "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (fit: int64 sums + f64 solve)", "data": "synthetic",
+              "config": config, "clocks": sampler.summary(),
+              "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": nbytes * n, "d2h_bytes_per_step": (H * W + 48 + (H // 16) * (W // 16) * 4 + 8) * n,
+                      "api": "motion.global_motion_estimation + get_motion_field_affine + compensate_frame + utils.PSNR per pair (results.py:50-59,109)"}},
+             real_stdout)
         return
 
     # ------------------------------------------------------------------ the B200 arm
@@ -466,7 +525,7 @@ def main():
                 "whole_step_algorithmic_gbs": sum(bytes_ps.values()) / (ms_total / args.steps * 1e-3) / 1e9}
     exhaustive = None
     try:
-        exhaustive = bench_exhaustive(D, N, torch, planes, dev)
+        exhaustive = bench_exhaustive(D, N, torch, planes, dev, float(sampler.max_mhz or 1965))
     except Exception as exc:                                                      # noqa: BLE001
         exhaustive = {"error": str(exc)}
     if l2_ref_ops_per_pair and isinstance(exhaustive, dict) and "probe_ssd_tops" in exhaustive:
@@ -474,8 +533,9 @@ def main():
         # on the full-resolution level per second, against the measured rate of the SSD instruction mix
         t = stages["bbme_l2"]["ms_per_step"] * 1e-3
         tops = l2_ref_ops_per_pair * pairs / t / 1e12
-        roofline["integer_pipe"] = {"kernel": "bbme_l2", "achieved": tops, "peak": exhaustive["probe_ssd_tops"],
-                                    "unit": "T pixel-pair ops/s", "frac": tops / exhaustive["probe_ssd_tops"],
+        roofline["integer_pipe"] = {"kernel": "bbme_l2", "achieved": tops, "peak": exhaustive["pipe_peak_tops"],
+                                    "unit": "T pixel-pair ops/s", "frac": tops / exhaustive["pipe_peak_tops"],
+                                    "frac_of_probe": tops / exhaustive["probe_ssd_tops"],
                                     "reference_ops_per_pair": l2_ref_ops_per_pair,
                                     "note": "operations the reference algorithm performs (oracle-instrumented); the kernel "
                                             "skips candidates whose cost it already holds"}
@@ -492,6 +552,17 @@ def main():
         cpu = {"value": v, "unit": unit, "cores": cores, "kind": "port",
                "sample": f"{n_cpu} pairs of the same sequence (cyclic), one pair per thread, {dt:.1f} s of wall time"}
 
+    dropin = None
+    if world == 1:
+        try:
+            fr = [np.ascontiguousarray(f) for f in host_frames.numpy()[:16 + DISTANCE]]
+            v, dt = dropin_pairs_per_s(fr, 16, reps=2)
+            dropin = {"value": v, "unit": unit, "sample": "16 pairs x 2 passes, one pair per call, NumPy in / NumPy out",
+                      "api": "motion.global_motion_estimation + get_motion_field_affine + compensate_frame + utils.PSNR "
+                             "(the calls of results.py:50-59,109)", "ms_per_pair": 1e3 / v}
+        except Exception as exc:                                                  # noqa: BLE001
+            dropin = {"error": str(exc)}
+
     out = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -503,7 +574,7 @@ def main():
                 "h2d_gbs": runner.h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
         "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
         "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "bbme_exhaustive": exhaustive,
-        "cpu_baseline": cpu, "parity": parity,
+        "cpu_baseline": cpu, "parity": parity, "dropin_per_pair": dropin,
     }
     emit(out, real_stdout)
     if world > 1:

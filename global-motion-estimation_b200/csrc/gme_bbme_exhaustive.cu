@@ -387,7 +387,7 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
                  make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h)) ? 1 : 0;
     if (!a.use_tma) memset(&map, 0, sizeof(map));
     auto kern = bbme_exhaustive2_kernel<BS, PNORM, SPLIT>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     dim3 grid((a.C + nb - 1) / nb, a.R, n);
     kern<<<grid, threads, smem, stream>>>(map, a, g);
     note_launch();
@@ -471,7 +471,7 @@ static int launch_fast(ExhaustiveArgs a, int n, cudaStream_t stream, bool *handl
                  make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h)) ? 1 : 0;
     if (!a.use_tma) memset(&map, 0, sizeof(map));
     auto kern = bbme_exhaustive_kernel<BS, PNORM, NT>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     dim3 grid((a.C + nb - 1) / nb, a.R, n);
     kern<<<grid, NT, smem, stream>>>(map, a);
     note_launch();
@@ -509,29 +509,46 @@ static int launch_exhaustive_pn(ExhaustiveArgs a, int n, int bs, cudaStream_t st
 
 // ---------------------------------------------------------------------------------------
 // Integer-pipe probe: the roofline denominator of the exhaustive search.  Every thread runs `iters` rounds of
-// eight independent packed cost updates (VABSDIFF4.ACC for SAD, VABSDIFF4 + IDP.4A for SSD) on registers --
-// no memory traffic -- so elapsed time gives the sustained pixel-pair rate of the instruction mix itself.
+// 4 x 8 independent packed cost updates (VABSDIFF4.ACC for SAD, VABSDIFF4 + IDP.4A for SSD) on registers -- no memory
+// traffic and NO other instruction in the loop body (round 1's probe refreshed an operand with SHF + LOP3 every eight
+// updates and so measured 8/10 of the pipe).  The second operand of every update is the accumulator of the neighbouring
+// chain, so no two updates see the same inputs: with loop-invariant operands ptxas merges the absolute differences of
+// the unrolled rounds and folds the dot products into a multiplication.
+// Elapsed time gives the sustained pixel-pair rate of the instruction mix itself; the ceiling of the pipe is
+// 148 SMs x 64 lanes x 4 pixels x f_SM (74.4 T pixel-pairs/s at 1965 MHz), bench.py reports both.
 // ---------------------------------------------------------------------------------------
+template <int PNORM>
+__device__ __forceinline__ uint32_t probe_update(uint32_t a, uint32_t b, uint32_t acc)
+{
+    uint32_t r;
+    if constexpr (PNORM == GME_PNORM_MAE) {
+        asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(acc));
+    } else {
+        uint32_t d;
+        asm volatile("vabsdiff4.u32.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0u));
+        asm volatile("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(d), "r"(d), "r"(acc));
+    }
+    return r;
+}
+
 template <int PNORM>
 __global__ void __launch_bounds__(256) sad_probe_kernel(uint32_t seed, int iters, uint32_t *out)
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t a[8], acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { a[k] = (tid + 1u) * 2654435761u + k * 0x9E3779B9u + seed; acc[k] = 0; }
-    uint32_t b = seed ^ (tid * 0x85EBCA6Bu);
+    for (int k = 0; k < 8; k++) { a[k] = (tid + 1u) * 2654435761u + k * 0x9E3779B9u + seed; acc[k] = seed ^ (tid * 0x85EBCA6Bu) ^ k; }
+#pragma unroll 4
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < 4; r++)
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = cost4_acc<PNORM>(a[k], b, acc[k]);
-            b = __funnelshift_l(b, b, 5) ^ a[r];
-        }
+            for (int k = 0; k < 8; k++) acc[k] = probe_update<PNORM>(a[(k + r) & 7], acc[(k + 1) & 7], acc[k]);
     }
     uint32_t t = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) t ^= acc[k];
-    if (t == 0x12345678u) out[tid & 1023] = t;          // keeps the chain alive; practically never taken
+    if (t == 0x12345678u) out[tid & 1023] = t;          // keeps the chains alive; practically never taken
 }
 
 int launch_sad_probe(int pnorm, int ctas, int iters, uint32_t *out, cudaStream_t stream)

@@ -33,6 +33,7 @@ struct PatternArgs {
     int margin;        // staged margin around the tile, pixels
     int win_w, win_h;  // staged window: win_w bytes per row (multiple of 16), win_h rows
     int use_tma;
+    int edge_tiles;    // dense diamond kernel: the clamped block columns (first, last two) are tiles of their own
     unsigned long long *sums;   // optional, [n][2]: per-plane sums of the two field channels (pipeline: the dense
                                 // first estimate, motion.py:186-188, is a mean -- no second pass over the field)
 };
@@ -213,6 +214,41 @@ __device__ __forceinline__ void sdsp_clamped(const E &e, int rmax, int cmax, int
 #pragma unroll
     for (int k = 0; k < 5; k++)
         if (cost[k] < best) { best = cost[k]; out_r = r[k]; out_c = c[k]; }
+}
+
+// Candidate-at-a-time evaluation for centres near the frame border, where the clamp of bbme.py:503-504 acts but every
+// (clamped) candidate still lies in the staged window: shared memory only, no inside test, no global-memory variant.
+// The general evaluator (any position, global memory when needed) is kept OUT of line: it is two orders of magnitude
+// rarer, and inlined into the walk it made every warp that held one border block run ~900 extra instructions.
+template <class E>
+struct WindowOnly {
+    const E &e;
+    template <int N>
+    __device__ __forceinline__ void eval(const int (&r)[N], const int (&c)[N], uint32_t (&cost)[N]) const
+    {
+        uint32_t part[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) part[k] = e.partial_smem(r[k], c[k]);
+#pragma unroll
+        for (int k = 0; k < N; k++) cost[k] = e.reduce(part[k]);
+    }
+};
+
+// (by value, results packed in the return value: taking the address of the evaluator or of the walk's position would
+// move them from registers to the stack in the hot loop as well)
+template <class E>
+__device__ __noinline__ int2 ldsp_step_cold(const E e, int rmax, int cmax, int mr, int mc)
+{
+    ldsp_step_clamped(e, rmax, cmax, mr, mc);      // the step stops exactly when the position does not move (bbme.py:512)
+    return make_int2(mr, mc);
+}
+
+template <class E>
+__device__ __noinline__ int2 sdsp_cold(const E e, int rmax, int cmax, int mr, int mc)
+{
+    int out_r, out_c;
+    sdsp_clamped(e, rmax, cmax, mr, mc, out_r, out_c);
+    return make_int2(out_r, out_c);
 }
 
 template <class E>
@@ -645,9 +681,13 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
     const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
     // centres for which the immediate-offset path applies: no clamp can act on the 5 x 5 neighbourhood of offsets, and
     // every word a candidate reads (16 + 2 rows, 16 + 2 columns + the word the funnel shift completes) is staged
-    D16Fast fast;
+    D16Fast fast, inwin;
     fast.r_lo = max(2, wr0 + 2); fast.r_hi = min(rmax - 2, wr0 + kD16Rows - BS - 2);
     fast.c_lo = max(2, wc0 + 2); fast.c_hi = min(cmax - 2, wc0 + kD16Pitch - BS - 2 - 7);
+    // centres whose clamped candidates all lie in the staged window (a clamped position lies between the centre and
+    // the unclamped one): the frame-border blocks
+    inwin.r_lo = wr0 + 2; inwin.r_hi = wr0 + kD16Rows - BS - 2;
+    inwin.c_lo = wc0 + 2; inwin.c_hi = wc0 + kD16Pitch - BS - 2 - 7;
     // this lane's first unit: row lane / 4, word lane % 4 (the second is eight rows below)
     const uint32_t lane_base = smem_u32(smem) + (uint32_t)((lane >> 2) * kD16Pitch + (lane & 3) * 4);
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
@@ -667,7 +707,16 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
         for (;;) {                                                 // LDSP, bbme.py:494-513
             if (kb == 0) {                                         // (re)start at (mr, mc)
                 if (!fast.ok(mr, mc)) {
-                    if (ldsp_step_clamped(e, rmax, cmax, mr, mc)) { last_fast = false; break; }
+                    bool stop;
+                    if (inwin.ok(mr, mc)) {
+                        stop = ldsp_step_clamped(WindowOnly<decltype(e)>{e}, rmax, cmax, mr, mc);
+                    } else {
+                        const int2 to = ldsp_step_cold(e, rmax, cmax, mr, mc);
+                        stop = to.x == mr && to.y == mc;
+                        mr = to.x;
+                        mc = to.y;
+                    }
+                    if (stop) { last_fast = false; break; }
                     continue;
                 }
                 xb = lane_base + (uint32_t)((mr - wr0) * kD16Pitch + (mc - wc0));
@@ -689,8 +738,12 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
             const int ks = (int)(d16_sdsp<PNORM>(c[0], xb, a0, a1) & 15u);
             out_r = mr + (int)((SRP >> (3 * ks)) & 7u) - 2;
             out_c = mc + (int)((SCP >> (3 * ks)) & 7u) - 2;
+        } else if (inwin.ok(mr, mc)) {
+            sdsp_clamped(WindowOnly<decltype(e)>{e}, rmax, cmax, mr, mc, out_r, out_c);
         } else {
-            sdsp_clamped(e, rmax, cmax, mr, mc, out_r, out_c);
+            const int2 o = sdsp_cold(e, rmax, cmax, mr, mc);
+            out_r = o.x;
+            out_c = o.y;
         }
         if (lane == 0)
             *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(out_c - bc, out_r - br);   // bbme.py:531-532
@@ -707,8 +760,14 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
 // scored with VABSDIFF4 (+ IDP.4A) against the anchor word.  The first minimum comes from a
 // min over (cost << 4 | index) keys.  The SDSP reuses the registers of the last LDSP step.  Steps
 // whose neighbourhood leaves the staged window or on which the clamp of bbme.py:503-504 could act
-// use the candidate-at-a-time evaluator (BlockEval<2, 1>).  The per-plane channel sums that the
-// first estimate needs are accumulated here (see PatternArgs::sums).
+// use the candidate-at-a-time evaluator (BlockEval<2, 1>).
+// The walks have different lengths, so a static block -> thread assignment leaves half of every
+// warp idle (round 1: 15.5 of 32 lanes active, profiles/r01k).  Here the kernel is ONE flat loop in
+// which every lane advances ITS block by one LDSP step per iteration; a lane whose block has
+// converged finishes it (SDSP, store) and takes the next block of the tile from a per-CTA queue
+// (one shared-memory atomic per warp and iteration, lanes ranked by ballot), so lanes only idle in
+// the tail of the tile.  The per-plane channel sums that the first estimate needs are accumulated
+// here (see PatternArgs::sums).
 // ---------------------------------------------------------------------------------------
 template <int PNORM, int NT>
 __global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
@@ -716,9 +775,21 @@ __global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant
     constexpr int BS = 2;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
+    __shared__ int next_block;
+    if (threadIdx.x == 0) next_block = 0;             // (stage_window synchronises the CTA before anyone reads it)
 
     const int plane = blockIdx.z;
-    const int tile_r = blockIdx.y * a.tby, tile_c = blockIdx.x * a.tbx;
+    // Tile columns: when the frame is wide enough (a.edge_tiles, set by the launcher), the block columns on which the clamp
+    // of bbme.py:503-504 acts -- the first one and the last two -- are tiles of their own.  Those blocks take the
+    // candidate-at-a-time evaluator; inside an ordinary tile they would be one or two lanes of every warp and make
+    // each of those warps run that (long) code with the other lanes idle.
+    constexpr int TBX = 64;                           // a.tbx of a full tile (index math by shifts)
+    const int tile_r = blockIdx.y * a.tby;
+    int tile_c, tw, shift = 6;                        // first block column, width, log2 of the queue's row stride
+    if (!a.edge_tiles) { tile_c = blockIdx.x * TBX; tw = min(TBX, a.C - tile_c); }
+    else if (blockIdx.x == 0) { tile_c = 0; tw = 1; shift = 0; }
+    else if (blockIdx.x == gridDim.x - 1) { tile_c = a.C - 2; tw = 2; shift = 1; }
+    else { tile_c = 1 + (blockIdx.x - 1) * TBX; tw = min(TBX, a.C - 2 - tile_c); }
     const int wr0 = tile_r * BS - a.margin, wc0 = (tile_c * BS - a.margin) & ~15;
     const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
     const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
@@ -737,7 +808,7 @@ __global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant
     e.lane_g = 0;
     e.gmask = 1u << (threadIdx.x & 31);
 
-    constexpr unsigned long long LRP = 0x321012342ull, LCP = 0x101234322ull;   // the same tables as nibbles (value + 2)
+    constexpr unsigned long long LRP = 0x321012342ull, LCP = 0x101234322ull;   // the LDSP / SDSP tables as nibbles (value + 2)
     constexpr unsigned SRP = 0x12322u, SCP = 0x21232u;
     const int rmax = a.H - BS - 1, cmax = a.W - BS - 1;        // bbme.py:503-504 (off by one, kept)
     // centres for which the register path applies: no clamp can act, and rows mr-2 .. mr+3 / the three aligned
@@ -746,77 +817,117 @@ __global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant
     const int fc_lo = max(2, wc0 + 2), fc_hi = min(cmax - 2, wc0 + 2 + a.win_w - 12);
     const uint32_t *win = reinterpret_cast<const uint32_t *>(smem);
     const int win_pw = a.win_w / 4;
+    const int lane = threadIdx.x & 31;
+    const int total = a.tby << shift;                            // queue entries: tby rows of 2^shift slots (slots >= tw are skipped)
+    const int rows_left = a.R - tile_r;                          // block rows of the frame this tile can hold
 
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
     int sum0 = 0, sum1 = 0;
-    for (int b = threadIdx.x; b < a.tbx * a.tby; b += NT) {
-        const int bi = tile_r + b / a.tbx, bj = tile_c + b % a.tbx;
-        if (bi >= a.R || bj >= a.C) continue;
-        const int br = bi * BS, bc = bj * BS;
-        e.load_anchor(prev_plane, br, bc);                       // anchor[0] = row 0 (2 bytes), anchor[1] = row 1
-        const uint32_t anchor = (e.anchor[0] & 0xFFFFu) | (e.anchor[1] << 16);
-
-        uint32_t z0[6], z1[6];                                   // row i: z0 = bytes 0..3, z1 = bytes 4..7 (byte 0 = column mc - 2)
-        auto cost_of = [&](uint32_t px) -> uint32_t { return cost4_acc<PNORM>(px, anchor, 0u); };
-        int mr = br, mc = bc;
-        bool last_fast = false;
-        uint32_t centre_cost = 0;
-        for (;;) {                                               // LDSP, bbme.py:494-513
-            if (mr >= fr_lo && mr <= fr_hi && mc >= fc_lo && mc <= fc_hi) {
-                const int x = mc - 2 - wc0;
-                const uint32_t *p = win + (mr - 2 - wr0) * win_pw + (x >> 2);
-                const int sh = (x & 3) * 8;
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const uint32_t w0 = p[i * win_pw], w1 = p[i * win_pw + 1], w2 = p[i * win_pw + 2];
-                    z0[i] = __funnelshift_r(w0, w1, sh);
-                    z1[i] = __funnelshift_r(w1, w2, sh);
+    bool active = false;                                         // this lane is walking a block
+    int bi = 0, bj = 0, br = 0, bc = 0, mr = 0, mc = 0;
+    uint32_t anchor = 0;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+        if (need) {                                              // hand the next blocks of the tile to the idle lanes
+            const int leader = __ffs(need) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&next_block, __popc(need));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!active) {
+                const int b = base + __popc(need & ((1u << lane) - 1u));
+                if (b < total) {
+                    const int lr = b >> shift, lc = b & ((1 << shift) - 1);
+                    if (lr < rows_left && lc < tw) {
+                        bi = tile_r + lr;
+                        bj = tile_c + lc;
+                        br = bi * BS;
+                        bc = bj * BS;
+                        const uint8_t *p = prev_plane + (unsigned)(br * (int)a.pitch + bc);   // 2-byte aligned: even column, pitch % 4 == 0
+                        anchor = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p)) |
+                                 ((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p + a.pitch)) << 16);
+                        e.anchor[0] = anchor & 0xFFFFu;
+                        e.anchor[1] = anchor >> 16;
+                        mr = br;
+                        mc = bc;
+                        active = true;
+                    }
                 }
-                // candidate (dr, dc): rows dr+2, dr+3; bytes dc+2, dc+3 of each
-                uint32_t c[9];
-                c[0] = cost_of(__byte_perm(z0[2], z0[3], 0x7632));                                            // ( 0,  0)
-                c[1] = cost_of(__byte_perm(z0[4], z0[5], 0x7632));                                            // ( 2,  0)
-                c[2] = cost_of(__byte_perm(__funnelshift_r(z0[3], z1[3], 24), __funnelshift_r(z0[4], z1[4], 24), 0x5410));   // ( 1,  1)
-                c[3] = cost_of(__byte_perm(z1[2], z1[3], 0x5410));                                            // ( 0,  2)
-                c[4] = cost_of(__byte_perm(__funnelshift_r(z0[1], z1[1], 24), __funnelshift_r(z0[2], z1[2], 24), 0x5410));   // (-1,  1)
-                c[5] = cost_of(__byte_perm(z0[0], z0[1], 0x7632));                                            // (-2,  0)
-                c[6] = cost_of(__byte_perm(z0[1], z0[2], 0x6521));                                            // (-1, -1)
-                c[7] = cost_of(__byte_perm(z0[2], z0[3], 0x5410));                                            // ( 0, -2)
-                c[8] = cost_of(__byte_perm(z0[3], z0[4], 0x6521));                                            // ( 1, -1)
-                uint32_t key = c[0] << 4;                        // first strict minimum in candidate order; costs < 2^18
+            }
+            if (base >= total && __ballot_sync(0xFFFFFFFFu, active) == 0) break;    // queue drained, nobody walking
+        }
+        if (!active) continue;
+
+        auto cost_of = [&](uint32_t px) -> uint32_t { return cost4_acc<PNORM>(px, anchor, 0u); };
+        int out_r, out_c;
+        bool done;
+        if (mr >= fr_lo && mr <= fr_hi && mc >= fc_lo && mc <= fc_hi) {      // one LDSP step, bbme.py:494-513
+            uint32_t z0[6], z1[6];                               // row i: z0 = bytes 0..3, z1 = bytes 4..7 (byte 0 = column mc - 2)
+            const int x = mc - 2 - wc0;
+            const uint32_t *p = win + (mr - 2 - wr0) * win_pw + (x >> 2);
+            const int sh = (x & 3) * 8;
 #pragma unroll
-                for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
-                const int kb = (int)(key & 15u);
-                if (kb == 0) { last_fast = true; centre_cost = c[0]; break; }
+            for (int i = 0; i < 6; i++) {
+                const uint32_t w0 = p[i * win_pw], w1 = p[i * win_pw + 1], w2 = p[i * win_pw + 2];
+                z0[i] = __funnelshift_r(w0, w1, sh);
+                z1[i] = __funnelshift_r(w1, w2, sh);
+            }
+            // candidate (dr, dc): rows dr+2, dr+3; bytes dc+2, dc+3 of each
+            uint32_t c[9];
+            c[0] = cost_of(__byte_perm(z0[2], z0[3], 0x7632));                                            // ( 0,  0)
+            c[1] = cost_of(__byte_perm(z0[4], z0[5], 0x7632));                                            // ( 2,  0)
+            c[2] = cost_of(__byte_perm(__funnelshift_r(z0[3], z1[3], 24), __funnelshift_r(z0[4], z1[4], 24), 0x5410));   // ( 1,  1)
+            c[3] = cost_of(__byte_perm(z1[2], z1[3], 0x5410));                                            // ( 0,  2)
+            c[4] = cost_of(__byte_perm(__funnelshift_r(z0[1], z1[1], 24), __funnelshift_r(z0[2], z1[2], 24), 0x5410));   // (-1,  1)
+            c[5] = cost_of(__byte_perm(z0[0], z0[1], 0x7632));                                            // (-2,  0)
+            c[6] = cost_of(__byte_perm(z0[1], z0[2], 0x6521));                                            // (-1, -1)
+            c[7] = cost_of(__byte_perm(z0[2], z0[3], 0x5410));                                            // ( 0, -2)
+            c[8] = cost_of(__byte_perm(z0[3], z0[4], 0x6521));                                            // ( 1, -1)
+            uint32_t key = c[0] << 4;                            // first strict minimum in candidate order; costs < 2^18
+#pragma unroll
+            for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
+            const int kb = (int)(key & 15u);
+            done = kb == 0;
+            if (done) {                                          // SDSP on the registers of this step, bbme.py:515-529
+                uint32_t ks = c[0] << 4;
+                ks = min(ks, (cost_of(__byte_perm(__funnelshift_r(z0[2], z1[2], 24), __funnelshift_r(z0[3], z1[3], 24), 0x5410)) << 4) | 1u);   // (0, +1)
+                ks = min(ks, (cost_of(__byte_perm(z0[3], z0[4], 0x7632)) << 4) | 2u);                     // (+1, 0)
+                ks = min(ks, (cost_of(__byte_perm(z0[2], z0[3], 0x6521)) << 4) | 3u);                     // (0, -1)
+                ks = min(ks, (cost_of(__byte_perm(z0[1], z0[2], 0x7632)) << 4) | 4u);                     // (-1, 0)
+                const int k = (int)(ks & 15u);
+                out_r = mr + (int)((SRP >> (4 * k)) & 15) - 2;
+                out_c = mc + (int)((SCP >> (4 * k)) & 15) - 2;
+            } else {
                 mr += (int)((LRP >> (4 * kb)) & 15) - 2;
                 mc += (int)((LCP >> (4 * kb)) & 15) - 2;
-            } else {
-                if (ldsp_step_clamped(e, rmax, cmax, mr, mc)) { last_fast = false; break; }
+            }
+        } else if (mr >= wr0 + 2 && mr <= wr0 + a.win_h - 4 && mc >= wc0 + 2 && mc <= wc0 + 2 + a.win_w - 12) {
+            // frame-border block: the clamp acts, but every clamped candidate is in the staged window
+            const WindowOnly<decltype(e)> w{e};
+            done = ldsp_step_clamped(w, rmax, cmax, mr, mc);
+            if (done) sdsp_clamped(w, rmax, cmax, mr, mc, out_r, out_c);
+        } else {
+            const int2 to = ldsp_step_cold(e, rmax, cmax, mr, mc);
+            done = to.x == mr && to.y == mc;
+            mr = to.x;
+            mc = to.y;
+            if (done) {
+                const int2 o = sdsp_cold(e, rmax, cmax, mr, mc);
+                out_r = o.x;
+                out_c = o.y;
             }
         }
-        int out_r, out_c;
-        if (last_fast) {                                         // SDSP on the registers of the last step
-            uint32_t key = centre_cost << 4;
-            key = min(key, (cost_of(__byte_perm(__funnelshift_r(z0[2], z1[2], 24), __funnelshift_r(z0[3], z1[3], 24), 0x5410)) << 4) | 1u);   // (0, +1)
-            key = min(key, (cost_of(__byte_perm(z0[3], z0[4], 0x7632)) << 4) | 2u);                           // (+1, 0)
-            key = min(key, (cost_of(__byte_perm(z0[2], z0[3], 0x6521)) << 4) | 3u);                           // (0, -1)
-            key = min(key, (cost_of(__byte_perm(z0[1], z0[2], 0x7632)) << 4) | 4u);                           // (-1, 0)
-            const int ks = (int)(key & 15u);
-            out_r = mr + (int)((SRP >> (4 * ks)) & 15) - 2;
-            out_c = mc + (int)((SCP >> (4 * ks)) & 15) - 2;
-        } else {
-            sdsp_clamped(e, rmax, cmax, mr, mc, out_r, out_c);
+        if (done) {
+            const int o0 = out_c - bc, o1 = out_r - br;          // bbme.py:531-532
+            *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(o0, o1);
+            sum0 += o0;
+            sum1 += o1;
+            active = false;
         }
-        const int o0 = out_c - bc, o1 = out_r - br;              // bbme.py:531-532
-        *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(o0, o1);
-        sum0 += o0;
-        sum1 += o1;
     }
     if (a.sums) {
-        __syncwarp();
         sum0 = __reduce_add_sync(0xFFFFFFFFu, sum0);
         sum1 = __reduce_add_sync(0xFFFFFFFFu, sum1);
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             if (sum0) atomicAdd(a.sums + 2 * plane, (unsigned long long)(long long)sum0);
             if (sum1) atomicAdd(a.sums + 2 * plane + 1, (unsigned long long)(long long)sum1);
         }
@@ -914,7 +1025,7 @@ static int launch_fast(PatternArgs a, int n, cudaStream_t stream)
     if (!a.use_tma) memset(&map, 0, sizeof(map));
     const size_t smem = (size_t)win_w * win_h + 32;      // slack for the trailing word of the last row
     auto kern = bbme_pattern_kernel<BS, G, PNORM, NT>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
     kern<<<grid, NT, smem, stream>>>(map, a);
     note_launch();
@@ -932,7 +1043,7 @@ static int launch_diamond16(PatternArgs a, int n, cudaStream_t stream)
     if (!a.use_tma) memset(&map, 0, sizeof(map));
     const size_t smem = (size_t)kD16Pitch * kD16Rows + 32;   // slack: the border evaluator's funnel shift reads one word past a row
     auto kern = bbme_diamond16_kernel<PNORM, NT>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
     kern<<<grid, NT, smem, stream>>>(map, a);
     note_launch();
@@ -943,8 +1054,11 @@ template <int PNORM>
 static int launch_diamond2(PatternArgs a, int n, cudaStream_t stream)
 {
     constexpr int NT = 256, BS = 2;
-    const int tbx = min(32, a.C), tby = min(16, a.R);
+    // 2048 blocks per CTA: the queue keeps the lanes busy until the tail of the tile, so the tile is large
+    const int tbx = 64, tby = min(32, a.R);              // (tbx is fixed in the kernel)
     const int margin = 12;
+    const int edge_tiles = a.C >= 8 ? 1 : 0;             // the clamped block columns (first, last two) as tiles of their own
+    a.edge_tiles = edge_tiles;
     int win_w = tbx * BS + 2 * margin + 4 + 15;
     win_w = (win_w + 15) / 16 * 16;
     if (win_w % 32 == 0) win_w += 16;
@@ -955,7 +1069,8 @@ static int launch_diamond2(PatternArgs a, int n, cudaStream_t stream)
     if (!a.use_tma) memset(&map, 0, sizeof(map));
     const size_t smem = (size_t)win_w * win_h + 32;
     auto kern = bbme_diamond2_kernel<PNORM, NT>;
-    dim3 grid((a.C + tbx - 1) / tbx, (a.R + tby - 1) / tby, n);
+    const int tiles_x = edge_tiles ? 2 + (a.C - 3 + tbx - 1) / tbx : (a.C + tbx - 1) / tbx;
+    dim3 grid(tiles_x, (a.R + tby - 1) / tby, n);
     kern<<<grid, NT, smem, stream>>>(map, a);
     note_launch();
     return check_launch("bbme_diamond2_kernel");

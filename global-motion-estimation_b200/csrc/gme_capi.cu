@@ -3,8 +3,11 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "gme_common.cuh"
@@ -33,7 +36,6 @@ int launch_sse(const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t,
 
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_last_cuda_error{0};
-static std::atomic<double> g_outlier_fraction{0.3};   // motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE (motion.py:10)
 
 // ---- per-stage timing (bench only) ----------------------------------------------------
 static std::mutex g_timing_mu;
@@ -69,6 +71,18 @@ struct StageTimer {
 };
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void ensure_dynamic_smem(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> granted;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &have = granted[{kernel, dev}];
+    if (bytes <= have) return;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess) have = bytes;
+}
 
 int check_launch(const char *what)
 {
@@ -198,13 +212,6 @@ int gme_last_cuda_error(void) { return g_last_cuda_error.load(); }
 
 uint64_t gme_launch_count(void) { return g_launches.load(); }
 
-int gme_pipeline_set_outlier_fraction(double pct)
-{
-    if (!(pct >= 0.0 && pct <= 1.0)) return GME_ERR_INVALID_ARGUMENT;
-    g_outlier_fraction.store(pct);
-    return GME_OK;
-}
-
 int gme_sad_peak_probe(int pnorm, int ctas, int iters, uint32_t *scratch, uint64_t *pixel_pairs, void *stream)
 {
     if (!scratch || !pixel_pairs || ctas <= 0 || iters <= 0 || pnorm < 0 || pnorm > 1) return GME_ERR_INVALID_ARGUMENT;
@@ -274,6 +281,7 @@ int gme_affine_fit(const int32_t *gt_field, int n, int R, int C, int level_h, in
                    int32_t *status, void *stream)
 {
     if (!gt_field || !params || n < 0 || level_h <= 0 || level_w <= 0) return GME_ERR_INVALID_ARGUMENT;
+    if (!(pct >= 0.0 && pct <= 1.0)) return GME_ERR_INVALID_ARGUMENT;   // also rejects NaN: int(pct * N) must lie in [0, N]
     if (R <= 0 || C <= 0) return GME_ERR_UNSUPPORTED;   // empty field: the reference indexes an empty array
     if ((long long)R * C > 0x7FFFFFFFLL) return GME_ERR_UNSUPPORTED;
     if (n == 0) return GME_OK;
@@ -363,11 +371,12 @@ void *gme_pipeline_workspace_ptr(void *workspace, int n, int H, int W, int which
 }
 
 int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *cur, size_t cur_plane_stride, int n,
-                 int H, int W, size_t pitch, int procedure, int search_window, double *params, uint8_t *comp,
-                 size_t comp_pitch, size_t comp_plane_stride, uint64_t *sse, int32_t *status, void *workspace,
-                 size_t workspace_bytes, void *stream)
+                 int H, int W, size_t pitch, int procedure, int search_window, double outlier_fraction, double *params,
+                 uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride, uint64_t *sse, int32_t *status,
+                 void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!prev || !cur || !params || !workspace || n < 0 || H <= 0 || W <= 0) return GME_ERR_INVALID_ARGUMENT;
+    if (!(outlier_fraction >= 0.0 && outlier_fraction <= 1.0)) return GME_ERR_INVALID_ARGUMENT;
     if (sse && !comp) return GME_ERR_INVALID_ARGUMENT;
     if (n == 0) return GME_OK;
     const Layout L = make_layout(n, H, W);
@@ -421,7 +430,7 @@ int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *c
     // the sequential part: first estimate, then project + robust fit per level (motion.py:128-134)
     // one launch: first estimate (mean of the dense field, from the channel sums) -> project + robust fit on L1 ->
     // project + robust fit on L2 -> model field of the final parameters at block_size 16 (results.py:52-54)
-    GME_TRY(launch_pipeline_fits(f1, L.R1, L.C1, L.l1.H, L.l1.W, out1, f2, L.R2, L.C2, H, W, out2, n, g_outlier_fraction.load(), params, status,
+    GME_TRY(launch_pipeline_fits(f1, L.R1, L.C1, L.l1.H, L.l1.W, out1, f2, L.R2, L.C2, H, W, out2, n, outlier_fraction, params, status,
                                  reinterpret_cast<const long long *>(sums), (long)L.R0 * L.C0, comp ? model : nullptr, st));
     timer.mark();
     if (comp) {

@@ -16,6 +16,8 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 // ---------------------------------------------------------------------------------------
 void note_launch();                 // counts kernel launches (gme_launch_count)
 int check_launch(const char *what); // cudaGetLastError -> GME_OK / GME_ERR_CUDA
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (kernel, device) and raised only when a launch needs more
+void ensure_dynamic_smem(const void *kernel, size_t bytes);
 
 // Builds a 3-D (W, H, n) uint8 tensor map with a (box_w, box_h, 1) box.  Returns false when
 // the planes cannot travel by TMA (alignment) -- callers then use the cooperative loader.

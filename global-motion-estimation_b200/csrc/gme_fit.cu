@@ -402,7 +402,7 @@ static int launch_fit(FitArgs &a, int n, cudaStream_t stream)
     for (int l = 0; l < a.nlevels; l++) want = max(want, (size_t)a.lv[l].R * a.lv[l].C * sizeof(unsigned int));
     a.cache_bytes = a.robust ? min(want, (size_t)160 * 1024) : 0;
     // per launch, not once per process: the attribute belongs to the current device's copy of the kernel
-    cudaFuncSetAttribute(affine_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    ensure_dynamic_smem(reinterpret_cast<const void *>(affine_fit_kernel), 160 * 1024);
     affine_fit_kernel<<<n, kFitBig, a.cache_bytes, stream>>>(a);
     note_launch();
     return check_launch("affine_fit_kernel");

@@ -22,6 +22,7 @@ import torch
 import gme_native as N
 
 PITCH_ALIGN = 16
+OUTLIER_FRACTION = .3            # motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE (motion.py:10)
 
 
 def require_cuda() -> torch.device:
@@ -217,7 +218,8 @@ def hierarchical_field(prev: Planes, cur: Planes, block_size: int, search_window
     return field
 
 
-def results_batch(frames: Planes, distance: int, procedure: int = N.SEARCH_DIAMOND, window: int = 2) -> dict:
+def results_batch(frames: Planes, distance: int, procedure: int = N.SEARCH_DIAMOND, window: int = 2,
+                  outlier_fraction: float = OUTLIER_FRACTION) -> dict:
     """Everything one iteration of the reference's results.py loop computes (results.py:47-59, 78-83, 109), for every
     pair (k, k + distance) of a device-resident sequence, left on the device: affine parameters, model field at block
     size 16, compensated previous frame, the two difference images and the squared-error sums behind the PSNR."""
@@ -226,7 +228,7 @@ def results_batch(frames: Planes, distance: int, procedure: int = N.SEARCH_DIAMO
         raise ValueError("sequence shorter than the frame distance")
     prev, cur = frames.view(0, n), frames.view(distance, distance + n)
     pipe = Pipeline(n, frames.H, frames.W, frames.t.device, want_comp=False)
-    pipe.run(prev, cur, procedure, window)
+    pipe.run(prev, cur, procedure, window, outlier_fraction)
     model = affine_field(pipe.params, frames.H // 16, frames.W // 16)
     comp, sse_, dprev, dcomp = compensate(prev, model, cur, want_diffs=True)
     return {"params": pipe.params, "status": pipe.status, "model_field": model, "compensated": comp, "sse": sse_,
@@ -268,29 +270,31 @@ class Pipeline:
         self.graph = None
         self._graph_key = None
 
-    def run(self, prev: Planes, cur: Planes, procedure: int = N.SEARCH_DIAMOND, window: int = 2):
+    def run(self, prev: Planes, cur: Planes, procedure: int = N.SEARCH_DIAMOND, window: int = 2,
+            outlier_fraction: float = OUTLIER_FRACTION):
         if prev.n != self.n or prev.H != self.H or prev.W != self.W or cur.t.shape != prev.t.shape:
             raise ValueError("pipeline geometry mismatch")
         if prev.pitch != cur.pitch:
             raise ValueError("previous and current must share one pitch")
         c = self.comp
         N.check(N.lib.gme_pipeline(prev.ptr, prev.stride, cur.ptr, cur.stride, self.n, self.H, self.W, prev.pitch,
-                                   int(procedure), int(window), self.params.data_ptr(),
+                                   int(procedure), int(window), float(outlier_fraction), self.params.data_ptr(),
                                    c.ptr if c else None, c.pitch if c else 0, c.stride if c else 0,
                                    self.sse.data_ptr() if c else None, self.status.data_ptr(),
                                    self.workspace.data_ptr(), self.workspace.numel(), _stream()), "gme_pipeline")
         return self.params, self.sse, self.status
 
-    def capture(self, prev: Planes, cur: Planes, procedure: int = N.SEARCH_DIAMOND, window: int = 2):
+    def capture(self, prev: Planes, cur: Planes, procedure: int = N.SEARCH_DIAMOND, window: int = 2,
+                outlier_fraction: float = OUTLIER_FRACTION):
         """Captures one run on (prev, cur) -- whose storage must stay alive and be refilled in place --
         into a CUDA graph; ``replay`` then costs one graph launch."""
-        self.run(prev, cur, procedure, window)            # warm-up outside capture (module load, attributes)
+        self.run(prev, cur, procedure, window, outlier_fraction)   # warm-up outside capture (module load, attributes)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run(prev, cur, procedure, window)
+            self.run(prev, cur, procedure, window, outlier_fraction)
         self.graph = g
-        self._graph_key = (prev.ptr, cur.ptr, procedure, window)
+        self._graph_key = (prev.ptr, cur.ptr, procedure, window, outlier_fraction)
         return g
 
     def replay(self):
@@ -318,13 +322,14 @@ class Pipeline:
         return [psnr_from_sse(int(s), self.H * self.W) for s in self.sse.cpu().tolist()]
 
 
-def gme_pairs(prev, cur, procedure: int = N.SEARCH_DIAMOND, window: int = 2, want_comp: bool = True):
+def gme_pairs(prev, cur, procedure: int = N.SEARCH_DIAMOND, window: int = 2, want_comp: bool = True,
+              outlier_fraction: float = OUTLIER_FRACTION):
     """Public batched entry point with HOST buffers: uint8 [n, H, W] previous and current frames in,
     (params float64[n, 6], psnr list, compensated uint8[n, H, W] | None) out.  Raises
     numpy.linalg.LinAlgError like the reference if any pair hits a singular normal matrix."""
     p, c = Planes.from_host(prev), Planes.from_host(cur)
     pipe = Pipeline(p.n, p.H, p.W, p.t.device, want_comp)
-    pipe.run(p, c, procedure, window)
+    pipe.run(p, c, procedure, window, outlier_fraction)
     if int(pipe.status.max().item()) != 0:
         raise N.singular_matrix_error()
     params = pipe.params.cpu().numpy()
@@ -343,6 +348,100 @@ def gme_sequence(frames: Planes, distance: int, procedure: int = N.SEARCH_DIAMON
     pipe = pipeline or Pipeline(n, frames.H, frames.W, frames.t.device)
     pipe.run(frames.view(0, n), frames.view(distance, distance + n), procedure, window)
     return pipe
+
+
+# --------------------------------------------------------------------------- the per-pair drop-in surface
+class PairSession:
+    """State behind the reference-facing per-pair calls (motion.global_motion_estimation, get_motion_field_affine,
+    compensate_frame, utils.PSNR -- what results.py:50-59,109 drives), one per frame geometry and device.
+
+    A call through the module surface costs host->device copies of its NumPy arguments, a handful of kernels on
+    KB..MB-scale data and a device->host read of its result, so everything that is not data movement is kept out of
+    it: the pipeline workspace, the device frame slots and the pinned staging buffers are allocated once; the frames
+    of a call travel as ONE copy from pinned memory; results come back through pinned buffers with ONE stream
+    synchronisation per call; the seven kernels of the pipeline are replayed from a CUDA graph.
+    Frames are NOT cached across calls by buffer identity: a caller may legally rewrite an array in place between
+    two calls, and verifying a cached copy (a host memcmp) costs as much as the pinned staging copy it would save.
+    """
+
+    def __init__(self, H: int, W: int, device=None):
+        self.device = device or require_cuda()
+        self.H, self.W = H, W
+        self.frames = Planes.empty(3, H, W, self.device)                 # slots: previous, current, (compensated input)
+        pitch = self.frames.pitch
+        self.stage = torch.empty((3, H, pitch), dtype=torch.uint8, pin_memory=True)
+        self.stage_np = self.stage.numpy()
+        self.pipe = Pipeline(1, H, W, self.device, want_comp=False)
+        self.out_host = torch.empty((8,), dtype=torch.float64, pin_memory=True)   # 6 parameters, status, spare
+        self.out_dev = torch.empty((8,), dtype=torch.float64, device=self.device)
+        self.sse_host = torch.empty((1,), dtype=torch.int64, pin_memory=True)
+        self.sse_dev = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        self.comp = Planes.empty(1, H, W, self.device)
+        self.comp_host = torch.empty((H, pitch), dtype=torch.uint8, pin_memory=True)
+        self.graphs = {}                                                   # (procedure, window, pct) -> CUDAGraph
+
+    def upload(self, *frames) -> None:
+        """frames[k] (uint8 ndarray [H, W]) -> device slot k; one pinned staging copy each, one H2D for all."""
+        for k, f in enumerate(frames):
+            self.stage_np[k, :, :self.W] = f
+        n = len(frames)
+        self.frames.t[:n].copy_(self.stage[:n], non_blocking=True)
+
+    def gme(self, previous, current, procedure: int, window: int, pct: float) -> np.ndarray:
+        self.upload(previous, current)
+        key = (int(procedure), int(window), float(pct))
+        prev, cur = self.frames.view(0, 1), self.frames.view(1, 2)
+        g = self.graphs.get(key)
+        if g is None:
+            self.pipe.run(prev, cur, *key)                                 # warm-up / validation outside capture
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.pipe.run(prev, cur, *key)
+                self.out_dev[:6] = self.pipe.params[0]
+                self.out_dev[6] = self.pipe.status[0].to(torch.float64)
+            self.graphs[key] = g
+        g.replay()
+        self.out_host.copy_(self.out_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if self.out_host[6].item() != 0:
+            raise N.singular_matrix_error()
+        return self.out_host[:6].numpy().copy()
+
+    def compensate(self, frame, field: np.ndarray) -> np.ndarray:
+        self.upload(frame)
+        f = torch.from_numpy(np.ascontiguousarray(field, dtype=np.int32)).unsqueeze(0).to(self.device, non_blocking=True)
+        n, R, C = f.shape[0], f.shape[1], f.shape[2]
+        src = self.frames.view(0, 1)
+        N.check(N.lib.gme_compensate(src.ptr, src.pitch, src.stride, f.data_ptr(), 0, R, C, None, 0, 0, self.comp.ptr,
+                                     self.comp.pitch, self.comp.stride, 1, self.H, self.W, None, _stream()), "gme_compensate")
+        self.comp_host.copy_(self.comp.t[0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.comp_host.numpy()[:, :self.W].copy()
+
+    def sse(self, a, b) -> int:
+        self.upload(a, b)
+        self.sse_dev.zero_()
+        x, y = self.frames.view(0, 1), self.frames.view(1, 2)
+        N.check(N.lib.gme_sse(x.ptr, x.pitch, x.stride, y.ptr, y.pitch, y.stride, 1, self.H, self.W,
+                              self.sse_dev.data_ptr(), _stream()), "gme_sse")
+        self.sse_host.copy_(self.sse_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(self.sse_host.item())
+
+
+_pair_sessions: dict = {}
+
+
+def pair_session(H: int, W: int) -> PairSession:
+    dev = require_cuda()
+    key = (H, W, dev.index)
+    s = _pair_sessions.get(key)
+    if s is None:
+        if len(_pair_sessions) >= 4:                                       # a handful of geometries at most stay resident
+            _pair_sessions.pop(next(iter(_pair_sessions)))
+        s = _pair_sessions[key] = PairSession(H, W, dev)
+    return s
 
 
 class HostSequenceRunner:

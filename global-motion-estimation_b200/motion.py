@@ -63,10 +63,14 @@ def global_motion_estimation(previous, current):
             parameters = parameter_projection(parameters)
             parameters = best_affine_parameters_robust(prev_pyr[i], curr_pyr[i], parameters)
         return parameters
-    _native.check(_native.lib.gme_pipeline_set_outlier_fraction(float(MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE)),
-                  "gme_pipeline_set_outlier_fraction")
-    params, _, _ = _dev.gme_pairs(np.asarray(previous)[None], np.asarray(current)[None],
-                                  procedure=BBME_SEARCHING_PROCEDURE, window=BBME_SEARCH_WINDOW, want_comp=False)
+    previous, current = np.asarray(previous), np.asarray(current)
+    if previous.ndim == 2 and previous.shape == current.shape and previous.dtype == current.dtype == np.uint8:
+        # the path results.py drives pair by pair: persistent per-geometry session (pinned staging, CUDA graph)
+        return _dev.pair_session(*previous.shape).gme(previous, current, BBME_SEARCHING_PROCEDURE, BBME_SEARCH_WINDOW,
+                                                      MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE)
+    params, _, _ = _dev.gme_pairs(previous[None], current[None],
+                                  procedure=BBME_SEARCHING_PROCEDURE, window=BBME_SEARCH_WINDOW, want_comp=False,
+                                  outlier_fraction=MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE)
     return params[0]
 
 
@@ -109,6 +113,8 @@ def compensate_frame(frame, motion_field):
         # a float field makes every index a float in the reference: each access raises inside its bare
         # try/except, so nothing is moved
         return np.copy(frame)
+    if frame.ndim == 2 and frame.dtype == np.uint8 and mf.ndim == 3 and mf.shape[0] > 0 and mf.shape[1] > 0:
+        return _dev.pair_session(*frame.shape).compensate(frame, mf[..., :2])
     dev = _dev.require_cuda()
     field = torch.from_numpy(np.ascontiguousarray(mf[..., :2], dtype=np.int32)).unsqueeze(0).to(dev)
     comp, _ = _dev.compensate(_dev.Planes.from_host(frame), field)

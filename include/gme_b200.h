@@ -10,12 +10,16 @@
  * Conventions
  *  - Every pointer is a DEVICE pointer owned by the caller (no ownership transfer, no
  *    allocation inside the library).  `stream` is a cudaStream_t passed as void*; all work
- *    is asynchronous on it.  Thread-safe for distinct streams/buffers.
+ *    is asynchronous on it.  Thread-safe for distinct streams/buffers: no entry point keeps
+ *    state between calls (the launch counter and the bench-only stage timer are the only
+ *    globals, both lock-protected).
  *  - A "plane set" is n grayscale uint8 planes of H rows x W columns: plane k starts at
  *    base + k*plane_stride, row r at + r*pitch (bytes).  pitch % 4 == 0 is required;
  *    pitch % 16 == 0 with 16-byte aligned bases lets the search windows travel by TMA
  *    (otherwise a cooperative-load path is used; results are identical).
  *    prev and cur may alias one sequence buffer (cur = prev + d*plane_stride).
+ *    Every plane must be backed by H*pitch readable bytes: the kernels read whole aligned
+ *    words, so the padding columns of the LAST row (bytes W..pitch-1) are touched too.
  *  - Motion fields are int32[n][R][C][2] with R = H/bs, C = W/bs; channel 0 = column
  *    (horizontal) displacement, channel 1 = row (vertical) displacement (bbme.py:176-177).
  *  - Return value: GME_OK, or a negative GME_ERR_* (never throws, never exits).
@@ -31,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GME_ABI_VERSION 1
+#define GME_ABI_VERSION 2   /* 2: gme_pipeline takes the outlier fraction; gme_pipeline_set_outlier_fraction is gone */
 
 #if defined(__GNUC__)
 #define GME_API __attribute__((visibility("default")))
@@ -83,6 +87,7 @@ GME_API int gme_first_parameters(const int32_t *dense_field, int n, int R, int C
 /* motion.best_affine_parameters_robust (motion.py:210-286) minus its BBME call, plus
  * motion.parameter_projection (motion.py:191-207) when project != 0:
  *   params (float64[n][6], in/out): old parameters in, new parameters out;
+ *   pct = motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE, in [0, 1] (GME_ERR_INVALID_ARGUMENT otherwise);
  *   robust = 0 gives motion.best_affine_parameters (motion.py:33-88, no outlier mask);
  *   level_h/level_w: shape of the frame the field was estimated on (w = 1/(h*w));
  *   outlier (uint8[n][R][C]), threshold (int32[n]), model_field (int16[n][R][C][2]) are
@@ -134,20 +139,19 @@ GME_API int gme_sse(const uint8_t *a, size_t a_pitch, size_t a_plane_stride,
  * procedure/search_window apply to the block_size-16 levels only; the dense first
  * estimate is always diamond with block_size 2 and the cost is always MSE, as in the
  * reference (motion.py:27-29, 224-229).  Reference behaviour = (GME_SEARCH_DIAMOND, 2).
+ * outlier_fraction = motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE (motion.py:10; reference: 0.3), the share of
+ * blocks the robust fits may flag; the reference keeps it as a module constant that users edit (README:137-141),
+ * the drop-in passes its current value with every call.  GME_ERR_INVALID_ARGUMENT outside [0, 1].
  * Outputs: params float64[n][6]; comp (optional) + sse uint64[n] (optional, needs comp);
  * status int32[n].  Workspace layout is private; size it with gme_pipeline_workspace_bytes. */
 GME_API size_t gme_pipeline_workspace_bytes(int n, int H, int W);
 GME_API int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride,
                  const uint8_t *cur, size_t cur_plane_stride,
                  int n, int H, int W, size_t pitch,
-                 int procedure, int search_window,
+                 int procedure, int search_window, double outlier_fraction,
                  double *params, uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride,
                  uint64_t *sse, int32_t *status,
                  void *workspace, size_t workspace_bytes, void *stream);
-
-/* motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE (motion.py:10) as used by gme_pipeline; 0.3 unless set.  The
- * reference keeps it as a module constant that users edit (README:137-141); the drop-in forwards its value here. */
-GME_API int gme_pipeline_set_outlier_fraction(double pct);
 
 /* Introspection for tests and the bench: pointers into a gme_pipeline workspace.
  * which: 0 dense L0 field, 1 L1 field, 2 L2 field (int32), 3 L1 outlier mask, 4 L2 outlier

@@ -24,7 +24,7 @@ def test_header_symbols_exported_and_bound():
 
 
 def test_version_and_error_strings():
-    assert N.ABI_VERSION == 1
+    assert N.ABI_VERSION == 2
     assert N.lib.gme_error_string(0) == b"ok"
     for code in (-1, -2, -3, -4, -5):
         assert N.lib.gme_error_string(code) not in (b"ok", b"unknown error")

@@ -143,3 +143,48 @@ def test_batched_api_equals_the_per_pair_driver_on_config3():
         model = O.get_motion_field_affine((seq.shape[1] // 16, seq.shape[2] // 16), want)
         np.testing.assert_array_equal(comp[k], O.compensate_frame(seq[k], model))
         assert str(psnr[k]) == fx["psnr_records"][str(k + d)]
+
+
+def test_streaming_results_dump_writes_the_same_tree(tmp_path):
+    """gme_results.dump_results -- decode thread -> pinned chunks -> batched kernels -> PNG encoder pool
+    -- writes, byte for byte, the tree the reference's results.py wrote for the config-3 clip."""
+    import make_results_golden as G
+    import gme_results
+    fx = _fixture("results_synth_pan")
+    seq = G.synth_frames()
+    clip = str(tmp_path / fx["clip"])
+    if not G.write_lossless_clip(clip, seq):
+        pytest.skip("no lossless (FFV1) video writer in this OpenCV build")
+    import utils
+    if G.frames_digest(utils.get_video_frames(clip)) != fx["frames_digest"]:
+        pytest.skip("the clip did not decode losslessly on this box")
+    out = str(tmp_path / "out")
+    os.makedirs(out)
+    t0 = time.perf_counter()
+    psnr = gme_results.dump_results(clip, os.path.join(out, ""), fx["distance"], chunk=16)
+    dt = time.perf_counter() - t0
+    assert list(psnr) == [str(k) for k in range(fx["distance"], fx["frames"])]      # the order results.py inserts them
+    _compare(out, fx)
+    print(f"streaming dump: {len(psnr)} pairs, {5 * len(psnr)} PNGs in {dt:.2f} s")
+
+
+def test_frame_prefetcher_equals_get_video_frames(tmp_path):
+    """The pinned-memory decoder yields exactly the frames utils.get_video_frames returns (utils.py:9-31), in order,
+    for chunk sizes that do and do not divide the frame count."""
+    import make_results_golden as G
+    import gme_results
+    import gme_synth as S
+    import utils
+    seq = S.pan_sequence(11, 96, 160, step=(2, 1), seed=9)
+    clip = str(tmp_path / "c.mp4")
+    if not G.write_lossless_clip(clip, seq):
+        pytest.skip("no lossless (FFV1) video writer in this OpenCV build")
+    want = utils.get_video_frames(clip)
+    for chunk in (4, 11, 16):
+        pf = gme_results.FramePrefetcher(clip, chunk=chunk)
+        got = []
+        for slot, frames, k in pf:
+            assert frames.is_pinned() and frames.shape[0] == k
+            got.extend(f.numpy().copy() for f in frames)
+            pf.release(slot)
+        assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
