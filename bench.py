@@ -398,15 +398,16 @@ def main():
     host_frames.copy_(seq)
     del seq
     prev, cur = planes.view(0, pairs), planes.view(DISTANCE, nf)
-    pipe = D.Pipeline(pairs, H, W, dev)
-    dev_out = torch.empty((pairs, 7), dtype=torch.float64, device=dev)
-    flush = None if "inputs larger" in config["l2_policy"] else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # Two pipelines (workspace + outputs) alternate between steps when there is a gather: the kernels write the
+    # [pairs, 7] rows (6 affine parameters + squared-error sum) straight into pipe.rows, the all-gather of step k runs on
+    # NCCL's stream while step k + 1 computes into the other set, and a set is reused only after its gather is done.
+    pipes = [D.Pipeline(pairs, H, W, dev) for _ in range(2 if world > 1 else 1)]
+    pipe = pipes[0]
     total_pairs = pairs * world
-
-    def rows():                                           # [pairs, 7]: 6 affine parameters + squared-error sum (-> PSNR)
-        dev_out[:, :6] = pipe.params
-        dev_out[:, 6] = pipe.sse
-        return dev_out
+    gathered = [torch.empty((total_pairs, 7), dtype=torch.float64, device=dev) for _ in pipes]
+    pending = [None for _ in pipes]
+    turn = [0]
+    flush = None if "inputs larger" in config["l2_policy"] else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     runner = D.HostSequenceRunner(nf, H, W, DISTANCE, chunk=max(1, -(-pairs // max(1, args.e2e_chunks))), procedure=procedure, window=window,
                                   device=dev)
@@ -420,11 +421,23 @@ def main():
             if world > 1:
                 GD.gather_rows(runner.dev_rows[:, :7], total_pairs)
             return out
-        pipe.run(prev, cur, procedure, window)          # results: pipe.params / pipe.sse / pipe.status / pipe.comp (device)
+        i = turn[0]
+        turn[0] = (i + 1) % len(pipes)
+        if pending[i] is not None:
+            pending[i].wait()                           # (stream-level) the gather that still reads this set's rows
+            pending[i] = None
+        pipes[i].run(prev, cur, procedure, window)      # results: .rows (.params / .sse) / .status / .comp on the device
         if world > 1:                                   # the only exchange of the path: [pairs, 7] rows to every rank
-            GD.gather_rows(rows(), total_pairs)
+            pending[i] = GD.gather_rows_async(pipes[i].rows, gathered[i])
+
+    def drain():                                        # orders the current stream after every gather still in flight
+        for i, w in enumerate(pending):
+            if w is not None:
+                w.wait()
+                pending[i] = None
 
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -440,6 +453,7 @@ def main():
             start.record()
             for _ in range(steps):
                 step(e2e)
+            drain()                                     # the last gathers belong to the timed region
             end.record()
             barrier()
         ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)

@@ -240,13 +240,13 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
             raw[i] = v;
         }
     }
+    // anchor blocks: one aligned 32-bit load per word (block columns are multiples of BS, BS % 4 == 0, planes and pitch
+    // are 4-byte aligned); the loads are in flight while the window travels
     for (int i = threadIdx.x; i < a.nb * BS * WPR; i += NT) {
         const int b = i / (BS * WPR), r = (i / WPR) % BS, w = i % WPR;
         uint32_t v = 0;
-        if (bj0 + b < a.C) {
-            const uint8_t *p = prev_plane + (size_t)(br + r) * a.pitch + (bc0 + b * BS) + 4 * w;
-            v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-        }
+        if (bj0 + b < a.C)
+            v = __ldg(reinterpret_cast<const uint32_t *>(prev_plane + (size_t)(br + r) * a.pitch + (bc0 + b * BS) + 4 * w));
         anchors[i] = v;
     }
     for (int i = threadIdx.x; i < a.nb; i += NT) keys[i] = ~0ull;
@@ -254,14 +254,23 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
     if (a.use_tma) mbar_wait(&bar, 0);
 
     // ---- four byte-shifted copies of the window ----------------------------------------------------------------
-    for (int i = threadIdx.x; i < a.win_h * g.cpitch; i += NT) {
-        const int r = i / g.cpitch, w = i - r * g.cpitch;
-        const uint32_t lo = w < g.rawpw ? raw[r * g.rawpw + w] : 0u;
-        const uint32_t hi = w + 1 < g.rawpw ? raw[r * g.rawpw + w + 1] : 0u;
-        copies[i] = lo;
-        copies[g.cstride + i] = __funnelshift_r(lo, hi, 8);
-        copies[2 * g.cstride + i] = __funnelshift_r(lo, hi, 16);
-        copies[3 * g.cstride + i] = __funnelshift_r(lo, hi, 24);
+    // a warp per window row, lanes over the words of the row: no index division, and the (up to two) words a lane
+    // expands per row are independent, so their shared-memory round trips overlap
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = NT >> 5;
+        for (int r = warp; r < a.win_h; r += nwarps) {
+            const uint32_t *src = raw + r * g.rawpw;
+            uint32_t *dst = copies + r * g.cpitch;
+#pragma unroll 2
+            for (int w = lane; w < g.cpitch; w += 32) {
+                const uint32_t lo = w < g.rawpw ? src[w] : 0u;
+                const uint32_t hi = w + 1 < g.rawpw ? src[w + 1] : 0u;
+                dst[w] = lo;
+                dst[g.cstride + w] = __funnelshift_r(lo, hi, 8);
+                dst[2 * g.cstride + w] = __funnelshift_r(lo, hi, 16);
+                dst[3 * g.cstride + w] = __funnelshift_r(lo, hi, 24);
+            }
+        }
     }
     __syncthreads();
 
@@ -346,7 +355,21 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
             best_key = k64 < best_key ? k64 : best_key;
         }
     }
-    if (best_key != ~0ull) atomicMin(&keys[bb], best_key);
+    // one 64-bit shared atomic per warp and macroblock instead of one per thread: when the whole warp works on one
+    // macroblock (the usual case) the keys are first reduced with shuffles
+    {
+        const int first_bb = __shfl_sync(0xFFFFFFFFu, bb, 0);
+        if (__all_sync(0xFFFFFFFFu, bb == first_bb)) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best_key, o);
+                best_key = other < best_key ? other : best_key;
+            }
+            if ((threadIdx.x & 31) == 0 && best_key != ~0ull) atomicMin(&keys[bb], best_key);
+        } else if (best_key != ~0ull) {
+            atomicMin(&keys[bb], best_key);
+        }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < a.nb; i += NT) {
         if (bj0 + i < a.C) {

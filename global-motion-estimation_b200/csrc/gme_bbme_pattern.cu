@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
 // here (see PatternArgs::sums).
 // ---------------------------------------------------------------------------------------
 template <int PNORM, int NT>
-__global__ void __launch_bounds__(NT) bbme_diamond2_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
+__global__ void __launch_bounds__(NT, 4) bbme_diamond2_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
 {
     constexpr int BS = 2;
     extern __shared__ __align__(128) uint8_t smem[];

@@ -26,10 +26,10 @@ int launch_affine_fit(const int32_t *, int, int, int, int, int, double, int, int
                       int16_t *, int32_t *, int, const long long *, long, cudaStream_t);
 int launch_affine_field(const double *, int, int, int, int16_t *, cudaStream_t);
 int launch_pipeline_fits(const int32_t *, int, int, int, int, uint8_t *, const int32_t *, int, int, int, int, uint8_t *,
-                         int, double, double *, int32_t *, const long long *, long, int16_t *, cudaStream_t);
+                         int, double, double *, int32_t *, const long long *, long, int16_t *, cudaStream_t, size_t);
 int launch_compensate(const uint8_t *, size_t, size_t, const void *, int, int, int, const uint8_t *, size_t, size_t,
                       uint8_t *, size_t, size_t, int, int, int, uint64_t *, cudaStream_t, uint8_t * = nullptr,
-                      uint8_t * = nullptr, size_t = 0, size_t = 0);
+                      uint8_t * = nullptr, size_t = 0, size_t = 0, size_t = 1);
 int launch_hier_merge(const void *, int, int, int, const int32_t *, int, int, int, double *, cudaStream_t);
 int launch_sse(const uint8_t *, size_t, size_t, const uint8_t *, size_t, size_t, int, int, int, uint64_t *,
                cudaStream_t);
@@ -372,9 +372,10 @@ void *gme_pipeline_workspace_ptr(void *workspace, int n, int H, int W, int which
 
 int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *cur, size_t cur_plane_stride, int n,
                  int H, int W, size_t pitch, int procedure, int search_window, double outlier_fraction, double *params,
-                 uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride, uint64_t *sse, int32_t *status,
-                 void *workspace, size_t workspace_bytes, void *stream)
+                 size_t params_stride, uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride, uint64_t *sse,
+                 size_t sse_stride, int32_t *status, void *workspace, size_t workspace_bytes, void *stream)
 {
+    if (params_stride < 6 || (sse && sse_stride < 1)) return GME_ERR_INVALID_ARGUMENT;
     if (!prev || !cur || !params || !workspace || n < 0 || H <= 0 || W <= 0) return GME_ERR_INVALID_ARGUMENT;
     if (!(outlier_fraction >= 0.0 && outlier_fraction <= 1.0)) return GME_ERR_INVALID_ARGUMENT;
     if (sse && !comp) return GME_ERR_INVALID_ARGUMENT;
@@ -431,12 +432,14 @@ int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride, const uint8_t *c
     // one launch: first estimate (mean of the dense field, from the channel sums) -> project + robust fit on L1 ->
     // project + robust fit on L2 -> model field of the final parameters at block_size 16 (results.py:52-54)
     GME_TRY(launch_pipeline_fits(f1, L.R1, L.C1, L.l1.H, L.l1.W, out1, f2, L.R2, L.C2, H, W, out2, n, outlier_fraction, params, status,
-                                 reinterpret_cast<const long long *>(sums), (long)L.R0 * L.C0, comp ? model : nullptr, st));
+                                 reinterpret_cast<const long long *>(sums), (long)L.R0 * L.C0, comp ? model : nullptr, st,
+                                 params_stride));
     timer.mark();
     if (comp) {
         // motion.compensate_frame of previous + the squared error against current (results.py:59,109)
         GME_TRY(launch_compensate(prev, pitch, prev_plane_stride, model, 1, L.R2, L.C2, sse ? cur : nullptr, pitch,
-                                  cur_plane_stride, comp, comp_pitch, comp_plane_stride, n, H, W, sse, st));
+                                  cur_plane_stride, comp, comp_pitch, comp_plane_stride, n, H, W, sse, st, nullptr, nullptr, 0,
+                                  0, sse ? sse_stride : 1));
     }
     timer.mark();
 #undef GME_TRY

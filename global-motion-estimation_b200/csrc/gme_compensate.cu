@@ -22,7 +22,7 @@ struct CompArgs {
     uint8_t *comp; size_t op, ostride;
     int H, W;
     int vec_ok;
-    unsigned long long *sse;
+    unsigned long long *sse; size_t sse_stride;   // squared-error sum of plane k at sse[k * sse_stride]
     uint8_t *dprev, *dcomp; size_t dp, dstride;   // optional |cur - frame| and |cur - comp| planes (results.py:78-83)
 };
 
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) compensate_kernel(CompArgs a)
             }
         }
     }
-    if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + plane);
+    if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + (size_t)plane * a.sse_stride);
 }
 
 // The case the pipeline runs (results.py:52-59): 16 x 16 blocks (BBME_BLOCK_SIZE), 16-byte aligned planes.  Same
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) compensate16_kernel(CompArgs a)
             }
         }
     }
-    if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + plane);
+    if (HAS_CUR) block_sum_u32_to_u64(err, a.sse + (size_t)plane * a.sse_stride);
 }
 
 // |x - y| per pixel (the difference images of results.py:78-83 when the fused kernel does not apply)
@@ -319,9 +319,10 @@ static inline bool aligned16(const void *p, size_t pitch, size_t stride)
 int launch_compensate(const uint8_t *frame, size_t fp, size_t fstride, const void *field, int field_is_i16, int R,
                       int C, const uint8_t *cur, size_t cp, size_t cstride, uint8_t *comp, size_t op, size_t ostride,
                       int n, int H, int W, uint64_t *sse, cudaStream_t stream, uint8_t *dprev = nullptr,
-                      uint8_t *dcomp = nullptr, size_t dp = 0, size_t dstride = 0)
+                      uint8_t *dcomp = nullptr, size_t dp = 0, size_t dstride = 0, size_t sse_stride = 1)
 {
     CompArgs a;
+    a.sse_stride = sse_stride;
     a.dprev = dprev; a.dcomp = dcomp; a.dp = dp; a.dstride = dstride;
     a.frame = frame; a.fp = fp; a.fstride = fstride;
     a.field = field; a.field_is_i16 = field_is_i16;
@@ -338,7 +339,8 @@ int launch_compensate(const uint8_t *frame, size_t fp, size_t fstride, const voi
     const bool diffs = dprev && dcomp && cur && sse;
     const bool fused_diffs = diffs && lean && aligned16(dprev, dp, dstride) && aligned16(dcomp, dp, dstride);
     if (cur && sse) {
-        cudaMemsetAsync(sse, 0, sizeof(uint64_t) * n, stream);
+        if (sse_stride == 1) cudaMemsetAsync(sse, 0, sizeof(uint64_t) * n, stream);
+        else cudaMemset2DAsync(sse, sse_stride * sizeof(uint64_t), 0, sizeof(uint64_t), n, stream);
         if (fused_diffs) compensate16_kernel<true, true><<<grid, block, 0, stream>>>(a);
         else if (lean) compensate16_kernel<true, false><<<grid, block, 0, stream>>>(a);
         else compensate_kernel<true><<<grid, block, 0, stream>>>(a);

@@ -94,6 +94,7 @@ struct FitArgs {
     double pct;              // MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE
     int robust, project;
     double *params;
+    size_t params_stride;    // doubles between the parameter rows of consecutive pairs (>= 6)
     int32_t *status;
     int status_or;           // OR into status instead of overwriting
     const long long *first_sums;   // pipeline: per-pair channel sums of the dense field (written by the dense
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
     __shared__ unsigned int sel_prefix, sel_rank, sh_dmax;
 
     const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *params = a.params + (size_t)pair * 6;
+    double *params = a.params + (size_t)pair * a.params_stride;
 
     if (tid < 6) {
         if (a.first_sums)   // motion.compute_first_parameters (motion.py:186-188): float64 mean, stored as float32
@@ -417,7 +418,7 @@ int launch_affine_fit(const int32_t *gt, int n, int R, int C, int level_h, int l
     a.lv[0] = FitLevel{gt, R, C, 1.0 / (double)((long long)level_h * level_w), outlier, threshold, model_field};
     a.nlevels = 1;
     a.pct = pct; a.robust = robust; a.project = project;
-    a.params = params; a.status = status; a.status_or = status_or;
+    a.params = params; a.params_stride = 6; a.status = status; a.status_or = status_or;
     a.first_sums = first_sums; a.first_count = first_count;
     a.final_field = nullptr;
     return launch_fit(a, n, stream);
@@ -427,14 +428,15 @@ int launch_affine_fit(const int32_t *gt, int n, int R, int C, int level_h, int l
 // on L1, projection + robust fit on L2 (motion.py:128-134), then the model field of the result (results.py:52-54).
 int launch_pipeline_fits(const int32_t *f1, int R1, int C1, int h1, int w1, uint8_t *out1, const int32_t *f2, int R2,
                          int C2, int h2, int w2, uint8_t *out2, int n, double pct, double *params, int32_t *status,
-                         const long long *first_sums, long first_count, int16_t *final_field, cudaStream_t stream)
+                         const long long *first_sums, long first_count, int16_t *final_field, cudaStream_t stream,
+                         size_t params_stride)
 {
     FitArgs a{};
     a.lv[0] = FitLevel{f1, R1, C1, 1.0 / (double)((long long)h1 * w1), out1, nullptr, nullptr};
     a.lv[1] = FitLevel{f2, R2, C2, 1.0 / (double)((long long)h2 * w2), out2, nullptr, nullptr};
     a.nlevels = 2;
     a.pct = pct; a.robust = 1; a.project = 1;
-    a.params = params; a.status = status; a.status_or = 1;
+    a.params = params; a.params_stride = params_stride; a.status = status; a.status_or = 1;
     a.first_sums = first_sums; a.first_count = first_count;
     a.final_field = final_field;
     return launch_fit(a, n, stream);

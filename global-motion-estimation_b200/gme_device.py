@@ -157,6 +157,7 @@ def affine_fit(gt_field: torch.Tensor, level_shape, params: torch.Tensor, robust
 
 
 def affine_field(params: torch.Tensor, R: int, C: int) -> torch.Tensor:
+    params = params.contiguous()                         # (Pipeline.params is a strided view of its row buffer)
     n = params.shape[0]
     field = torch.zeros((n, R, C, 2), dtype=torch.int16, device=params.device)
     N.check(N.lib.gme_affine_field(params.data_ptr(), n, R, C, field.data_ptr(), _stream()), "gme_affine_field")
@@ -263,10 +264,13 @@ class Pipeline:
         self.n, self.H, self.W = n, H, W
         nbytes = N.lib.gme_pipeline_workspace_bytes(n, H, W)
         self.workspace = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=self.device)
-        self.params = torch.zeros((n, 6), dtype=torch.float64, device=self.device)
+        # one row of seven 8-byte words per pair: six float64 parameters + the uint64 squared-error sum.  The kernels
+        # write both straight into it (strided outputs of gme_pipeline), so the multi-GPU gather ships `rows` as is.
+        self.rows = torch.zeros((n, 7), dtype=torch.float64, device=self.device)
+        self.params = self.rows[:, :6]
         self.status = torch.zeros((n,), dtype=torch.int32, device=self.device)
         self.comp = Planes.empty(n, H, W, self.device) if want_comp else None
-        self.sse = torch.zeros((n,), dtype=torch.int64, device=self.device) if want_comp else None
+        self.sse = self.rows.view(torch.int64)[:, 6] if want_comp else None
         self.graph = None
         self._graph_key = None
 
@@ -278,9 +282,9 @@ class Pipeline:
             raise ValueError("previous and current must share one pitch")
         c = self.comp
         N.check(N.lib.gme_pipeline(prev.ptr, prev.stride, cur.ptr, cur.stride, self.n, self.H, self.W, prev.pitch,
-                                   int(procedure), int(window), float(outlier_fraction), self.params.data_ptr(),
+                                   int(procedure), int(window), float(outlier_fraction), self.params.data_ptr(), 7,
                                    c.ptr if c else None, c.pitch if c else 0, c.stride if c else 0,
-                                   self.sse.data_ptr() if c else None, self.status.data_ptr(),
+                                   self.sse.data_ptr() if c else None, 7, self.status.data_ptr(),
                                    self.workspace.data_ptr(), self.workspace.numel(), _stream()), "gme_pipeline")
         return self.params, self.sse, self.status
 

@@ -45,6 +45,14 @@ def gather_rows(local: torch.Tensor, n_pairs: int, group=None) -> torch.Tensor:
     return torch.cat(rows, 0)
 
 
+def gather_rows_async(local: torch.Tensor, out: torch.Tensor, group=None):
+    """Equal shards, NCCL: starts ONE all_gather_into_tensor of this rank's contiguous [n_local, k] rows into
+    ``out`` ([world * n_local, k]) on NCCL's own stream and returns the work handle.  The collective waits for the
+    kernels already enqueued on the current stream, but nothing enqueued afterwards waits for it: the next batch's
+    kernels run while the rows travel.  ``work.wait()`` orders the current stream after the gather."""
+    return dist.all_gather_into_tensor(out, local, group=group, async_op=True)
+
+
 def run_sharded(n_pairs: int, compute, group=None) -> torch.Tensor:
     """compute(start, stop) -> float64[stop - start, k] for this rank's pairs; returns all rows on all ranks."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)

@@ -39,7 +39,7 @@ SYMBOLS = {
     "gme_hier_merge": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
     "gme_sse": (_i, [_p, _sz, _sz, _p, _sz, _sz, _i, _i, _i, _p, _p]),
     "gme_pipeline_workspace_bytes": (_sz, [_i, _i, _i]),
-    "gme_pipeline": (_i, [_p, _sz, _p, _sz, _i, _i, _i, _sz, _i, _i, _d, _p, _p, _sz, _sz, _p, _p, _p, _sz, _p]),
+    "gme_pipeline": (_i, [_p, _sz, _p, _sz, _i, _i, _i, _sz, _i, _i, _d, _p, _sz, _p, _sz, _sz, _p, _sz, _p, _p, _sz, _p]),
     "gme_pipeline_workspace_ptr": (_p, [_p, _i, _i, _i, _i]),
     "gme_stage_timing_enable": (_i, [_i]),
     "gme_stage_timing_read": (_i, [_p, _p]),

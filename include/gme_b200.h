@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GME_ABI_VERSION 2   /* 2: gme_pipeline takes the outlier fraction; gme_pipeline_set_outlier_fraction is gone */
+#define GME_ABI_VERSION 2   /* 2: gme_pipeline takes the outlier fraction and output strides; gme_pipeline_set_outlier_fraction is gone */
 
 #if defined(__GNUC__)
 #define GME_API __attribute__((visibility("default")))
@@ -142,15 +142,18 @@ GME_API int gme_sse(const uint8_t *a, size_t a_pitch, size_t a_plane_stride,
  * outlier_fraction = motion.MOTION_VECTOR_ERROR_THRESHOLD_PERCENTAGE (motion.py:10; reference: 0.3), the share of
  * blocks the robust fits may flag; the reference keeps it as a module constant that users edit (README:137-141),
  * the drop-in passes its current value with every call.  GME_ERR_INVALID_ARGUMENT outside [0, 1].
- * Outputs: params float64[n][6]; comp (optional) + sse uint64[n] (optional, needs comp);
- * status int32[n].  Workspace layout is private; size it with gme_pipeline_workspace_bytes. */
+ * Outputs: params float64[n][6], pair k at params + k*params_stride doubles (params_stride >= 6); comp (optional)
+ * + sse (optional, needs comp), pair k at sse + k*sse_stride uint64 words; status int32[n].  The strides let the
+ * caller interleave both into ONE row buffer ([n][7] 8-byte words: six parameters + the squared error), which is what
+ * the multi-GPU path gathers -- no packing kernel between the pipeline and the collective.  Workspace layout is private; size it with gme_pipeline_workspace_bytes. */
 GME_API size_t gme_pipeline_workspace_bytes(int n, int H, int W);
 GME_API int gme_pipeline(const uint8_t *prev, size_t prev_plane_stride,
                  const uint8_t *cur, size_t cur_plane_stride,
                  int n, int H, int W, size_t pitch,
                  int procedure, int search_window, double outlier_fraction,
-                 double *params, uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride,
-                 uint64_t *sse, int32_t *status,
+                 double *params, size_t params_stride,
+                 uint8_t *comp, size_t comp_pitch, size_t comp_plane_stride,
+                 uint64_t *sse, size_t sse_stride, int32_t *status,
                  void *workspace, size_t workspace_bytes, void *stream);
 
 /* Introspection for tests and the bench: pointers into a gme_pipeline workspace.

@@ -70,11 +70,17 @@ def _rounding_tie(inter, final=None, final_shape=None, eps=1e-9):
         p[0] *= 2
         p[3] *= 2
         R, C = inter[level]["gt"].shape[:2]
-        if _near_half(p, R, C, eps):
+        # level 1 starts from the first estimate [2*float32(mean), 0, 0, ...]: a0 + 0*i + 0*j is EXACT in float64, so a
+        # tie there is an exact .5 that round-half-even resolves identically everywhere -- a hard check, never skipped
+        exact = level == 1 and not p[[1, 2, 4, 5]].any()
+        if not exact and _near_half(p, R, C, eps):
             return True
         prev = np.asarray(inter[level]["params"], dtype=np.float64)
     # ... and the model field of the FINAL parameters, which steers the compensation (results.py:52-54)
     return final is not None and _near_half(np.asarray(final, dtype=np.float64), final_shape[0], final_shape[1], eps)
+
+
+_TIES = {"pairs": 0, "skipped": 0}
 
 
 @pytest.mark.parametrize("seed", range(6 * SCALE))
@@ -91,10 +97,19 @@ def test_pipeline_fuzz(D, seed):
         want, inter = O.global_motion_estimation(seq[k], seq[k + d], procedure=sp, window=sw, return_intermediates=True)
         np.testing.assert_array_equal(pipe.intermediate(0)[k].cpu().numpy(), inter[0]["dense"])
         np.testing.assert_array_equal(pipe.intermediate(2)[k].cpu().numpy(), inter[2]["gt"])
+        _TIES["pairs"] += 1
         if _rounding_tie(inter, want, (H // 16, W // 16)):
+            _TIES["skipped"] += 1
             continue      # a model vector sits on a .5 tie: float64 round-off decides it, in the reference too
         np.testing.assert_array_equal(pipe.intermediate(4)[k].cpu().numpy().astype(bool), inter[2]["outlier"])
         np.testing.assert_allclose(pipe.params[k].cpu().numpy(), want, **PARAM_TOL)
         comp = O.compensate_frame(seq[k], O.get_motion_field_affine((H // 16, W // 16), want))
         np.testing.assert_array_equal(pipe.comp.to_host()[k], comp)
         assert int(pipe.sse[k].item()) == O.sse(seq[k + d], comp)
+
+
+def test_rounding_tie_skips_stay_rare():
+    """(runs after test_pipeline_fuzz) the float comparisons may be skipped only for the rare pairs whose model vector
+    sits on an inexact .5 tie; if that ever becomes common the guard is hiding something."""
+    assert _TIES["pairs"] > 0
+    assert _TIES["skipped"] <= max(1, _TIES["pairs"] // 20), _TIES
