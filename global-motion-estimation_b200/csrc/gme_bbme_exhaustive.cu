@@ -35,6 +35,8 @@ struct ExhaustiveArgs {
     int tpb;            // threads per macroblock (<= ncand)
     int win_w, win_h;   // staged window (bytes per row, rows)
     int use_tma;
+    int strips_x;       // second-generation kernel: strips per block row, and strips in all (planes x block rows x strips_x)
+    int strips;
 };
 
 template <int BS, int PNORM, int NT>
@@ -190,6 +192,7 @@ struct Exhaustive2Geom {
     int rawpw;        // raw window pitch, words
     int cpitch;       // shifted-copy row pitch, words (= 2 mod 4)
     int cstride;      // words between the four copies (= 4 mod 32)
+    unsigned cpitch_rcp;   // ceil(2^32 / cpitch): i / cpitch == umulhi(i, cpitch_rcp) for i < 2^32 / cpitch
 };
 
 template <int BS, int PNORM, int SPLIT>
@@ -199,34 +202,87 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
     static_assert(BS % 4 == 0 && BS >= 8 && (SPLIT == 1 || SPLIT == 2), "block sizes 8, 12, 16");
     constexpr int WPR = BS / 4, HB = BS / SPLIT;     // HB anchor rows per thread
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
 
     const int NT = blockDim.x;
-    const int plane = blockIdx.z, bi = blockIdx.y, bj0 = blockIdx.x * a.nb;
-    const int br = bi * BS, bc0 = bj0 * BS;
     const int ncand = 2 * a.sw + BS;
+    const size_t raw_bytes = ((size_t)a.win_w * a.win_h + 127) / 128 * 128;
+    uint32_t *copies = reinterpret_cast<uint32_t *>(smem + 2 * raw_bytes);                           // [4][cstride]
+    const int nanc = a.nb * BS * WPR + (a.nb * BS * WPR & 1);                                        // words per anchor buffer
+    uint32_t *anchors2 = copies + 4 * g.cstride;                                                     // [2][nb][BS][WPR]
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(anchors2 + 2 * nanc);
+    constexpr int KA = (WPR + SPLIT - 1) / SPLIT;       // anchor words a thread fetches per strip: nb*BS*WPR <= KA * blockDim.x
+
+    // Persistent CTA: it walks the strips t = blockIdx.x, blockIdx.x + gridDim.x, ... (strip = nb macroblocks of one block
+    // row of one plane) and keeps TWO raw windows: while strip t is searched, the window of the next strip is already
+    // travelling by TMA into the other buffer (its own mbarrier, phase = use count mod 2).  One strip per CTA spent half
+    // of a CTA's lifetime in launch, TMA latency and drain with only two CTAs per SM to hide it (profiles/r01k).
+    auto strip_origin = [&](int t, int &plane, int &bi, int &bj0) {
+        const int row = t / a.strips_x;
+        bj0 = (t - row * a.strips_x) * a.nb;
+        plane = row / a.R;
+        bi = row - plane * a.R;
+    };
+    auto issue_window = [&](int t, int buf) {                    // one thread: TMA of strip t's window into raw[buf]
+        int plane, bi, bj0;
+        strip_origin(t, plane, bi, bj0);
+        fence_proxy_async();                                     // the buffer was read through the generic proxy before
+        mbar_arrive_expect_tx(&bar[buf], (uint32_t)(a.win_w * a.win_h));
+        tma_load_3d(smem + buf * raw_bytes, &cur_map, &bar[buf], (bj0 * BS - a.sw) & ~15, bi * BS - a.sw, plane);
+    };
+    // the anchor blocks of strip t, KA words per thread: one aligned 32-bit load per word (block columns are multiples
+    // of BS, BS % 4 == 0, planes and pitch are 4-byte aligned)
+    auto fetch_anchors = [&](int t, uint32_t (&v)[KA]) {
+        int plane, bi, bj0;
+        strip_origin(t, plane, bi, bj0);
+        const uint8_t *pp = a.prev + (size_t)plane * a.prev_stride + (size_t)(bi * BS) * a.pitch + bj0 * BS;
+#pragma unroll
+        for (int k = 0; k < KA; k++) {
+            const int i = threadIdx.x + k * NT;
+            v[k] = 0;
+            if (i < a.nb * BS * WPR) {
+                const int b = i / (BS * WPR), r = (i / WPR) % BS, w = i % WPR;
+                if (bj0 + b < a.C) v[k] = __ldg(reinterpret_cast<const uint32_t *>(pp + (size_t)r * a.pitch + b * BS + 4 * w));
+            }
+        }
+    };
+    auto store_anchors = [&](uint32_t *dst, const uint32_t (&v)[KA]) {
+#pragma unroll
+        for (int k = 0; k < KA; k++) {
+            const int i = threadIdx.x + k * NT;
+            if (i < a.nb * BS * WPR) dst[i] = v[k];
+        }
+    };
+    if (a.use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && (int)blockIdx.x < a.strips) issue_window(blockIdx.x, 0);
+    }
+    if ((int)blockIdx.x < a.strips) {
+        uint32_t v[KA];
+        fetch_anchors(blockIdx.x, v);
+        store_anchors(anchors2, v);
+    }
+
+    for (int it = 0, t = blockIdx.x; t < a.strips; ++it, t += gridDim.x) {
+    const int buf = it & 1;
+    int plane, bi, bj0;
+    strip_origin(t, plane, bi, bj0);
+    const int br = bi * BS, bc0 = bj0 * BS;
     const int wr0 = br - a.sw, wc0 = (bc0 - a.sw) & ~15;         // TMA: 16-byte aligned first column
     const int xoff = (bc0 - a.sw) - wc0;
     const uint8_t *prev_plane = a.prev + (size_t)plane * a.prev_stride;
     const uint8_t *cur_plane = a.cur + (size_t)plane * a.cur_stride;
+    uint32_t *raw = reinterpret_cast<uint32_t *>(smem + buf * raw_bytes);
 
-    uint32_t *raw = reinterpret_cast<uint32_t *>(smem);
-    const size_t raw_bytes = ((size_t)a.win_w * a.win_h + 127) / 128 * 128;
-    uint32_t *copies = reinterpret_cast<uint32_t *>(smem + raw_bytes);                               // [4][cstride]
-    uint32_t *anchors = copies + 4 * g.cstride;                                                      // [nb][BS][WPR]
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(anchors + a.nb * BS * WPR + (a.nb * BS * WPR & 1));
-
-    // ---- stage: raw window (TMA), anchor blocks, result keys ----------------------------------------------
+    // ---- stage: raw window (TMA, already in flight; the next strip's is issued now), anchor blocks, result keys ----
     if (a.use_tma) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&bar, (uint32_t)(a.win_w * a.win_h));
-            tma_load_3d(smem, &cur_map, &bar, wc0, wr0, plane);
-        }
+        // raw[buf ^ 1] was last read by the copy expansion of the previous strip, which every thread has left
+        if (threadIdx.x == 0 && t + (int)gridDim.x < a.strips) issue_window(t + gridDim.x, buf ^ 1);
     } else {
         for (int i = threadIdx.x; i < g.rawpw * a.win_h; i += NT) {
             const int rr = wr0 + i / g.rawpw, cc = wc0 + (i % g.rawpw) * 4;
@@ -240,37 +296,27 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
             raw[i] = v;
         }
     }
-    // anchor blocks: one aligned 32-bit load per word (block columns are multiples of BS, BS % 4 == 0, planes and pitch
-    // are 4-byte aligned); the loads are in flight while the window travels
-    for (int i = threadIdx.x; i < a.nb * BS * WPR; i += NT) {
-        const int b = i / (BS * WPR), r = (i / WPR) % BS, w = i % WPR;
-        uint32_t v = 0;
-        if (bj0 + b < a.C)
-            v = __ldg(reinterpret_cast<const uint32_t *>(prev_plane + (size_t)(br + r) * a.pitch + (bc0 + b * BS) + 4 * w));
-        anchors[i] = v;
-    }
+    // anchor blocks: this strip's are in anchors2[buf] already (fetched while the previous strip was searched); the next
+    // strip's are requested now and stored after the search, so their global-memory latency never shows
+    uint32_t *anchors = anchors2 + buf * nanc;
+    const bool has_next = t + (int)gridDim.x < a.strips;
+    uint32_t next_anc[KA];
+    if (has_next) fetch_anchors(t + gridDim.x, next_anc);
     for (int i = threadIdx.x; i < a.nb; i += NT) keys[i] = ~0ull;
     __syncthreads();
-    if (a.use_tma) mbar_wait(&bar, 0);
+    if (a.use_tma) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
 
     // ---- four byte-shifted copies of the window ----------------------------------------------------------------
-    // a warp per window row, lanes over the words of the row: no index division, and the (up to two) words a lane
-    // expands per row are independent, so their shared-memory round trips overlap
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = NT >> 5;
-        for (int r = warp; r < a.win_h; r += nwarps) {
-            const uint32_t *src = raw + r * g.rawpw;
-            uint32_t *dst = copies + r * g.cpitch;
-#pragma unroll 2
-            for (int w = lane; w < g.cpitch; w += 32) {
-                const uint32_t lo = w < g.rawpw ? src[w] : 0u;
-                const uint32_t hi = w + 1 < g.rawpw ? src[w + 1] : 0u;
-                dst[w] = lo;
-                dst[g.cstride + w] = __funnelshift_r(lo, hi, 8);
-                dst[2 * g.cstride + w] = __funnelshift_r(lo, hi, 16);
-                dst[3 * g.cstride + w] = __funnelshift_r(lo, hi, 24);
-            }
-        }
+    // (flat index over rows x words; the row comes from a multiply-high with the host's reciprocal of cpitch, exact
+    // for every index of a window: a 32-bit division per element made this loop a quarter of a CTA's lifetime)
+    for (int i = threadIdx.x; i < a.win_h * g.cpitch; i += NT) {
+        const int r = (int)__umulhi((unsigned)i, g.cpitch_rcp), w = i - r * g.cpitch;
+        const uint32_t lo = w < g.rawpw ? raw[r * g.rawpw + w] : 0u;
+        const uint32_t hi = w + 1 < g.rawpw ? raw[r * g.rawpw + w + 1] : 0u;
+        copies[i] = lo;
+        copies[g.cstride + i] = __funnelshift_r(lo, hi, 8);
+        copies[2 * g.cstride + i] = __funnelshift_r(lo, hi, 16);
+        copies[3 * g.cstride + i] = __funnelshift_r(lo, hi, 24);
     }
     __syncthreads();
 
@@ -380,6 +426,9 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
             f[1] = j - a.sw;       // row offset    -> channel 1 (bbme.py:177)
         }
     }
+    if (has_next) store_anchors(anchors2 + (buf ^ 1) * nanc, next_anc);
+    __syncthreads();               // keys and copies are rewritten by the next strip, which also reads the new anchors
+    }   // strips
 }
 
 template <int BS, int PNORM>
@@ -393,7 +442,8 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     if (ncand > 256) return GME_OK;                              // key packs the row index in 8 bits
     Exhaustive2Geom g;
     g.tpb = min(ncand, 384 / SPLIT);
-    const int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
+    int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
+    nb = (a.C + (a.C + nb - 1) / nb - 1) / ((a.C + nb - 1) / nb);   // same number of strips per block row, evenly filled
     const int threads = (nb * g.tpb * SPLIT + 31) / 32 * 32;
     const int win_h = 2 * a.sw + 2 * BS - 1;
     int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4 + 15;  // +15: the first column is rounded down to 16 bytes
@@ -401,9 +451,10 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     g.rawpw = win_w / 4;
     g.cpitch = g.rawpw + 2;                                      // rawpw = 0 (mod 4)  ->  2 (mod 4)
     g.cstride = (win_h * g.cpitch + 31) / 32 * 32 + (SPLIT == 2 ? 4 : 8);   // 4 (mod 32); one thread per column: 8
+    g.cpitch_rcp = (unsigned)((0x100000000ull + g.cpitch - 1) / g.cpitch);
     const size_t raw_bytes = ((size_t)win_w * win_h + 127) / 128 * 128;
-    const size_t smem = raw_bytes + (size_t)4 * g.cstride * 4 + (size_t)(nb * BS * WPR + 1) * 4 + (size_t)nb * 8 + 16;
-    if (smem > 100 * 1024) return GME_OK;                        // window too large: previous kernel / generic path
+    const size_t smem = 2 * raw_bytes + (size_t)4 * g.cstride * 4 + (size_t)2 * (nb * BS * WPR + 1) * 4 + (size_t)nb * 8 + 16;
+    if (smem > 110 * 1024) return GME_OK;                        // window too large: previous kernel / generic path
     a.nb = nb; a.tpb = g.tpb; a.win_w = win_w; a.win_h = win_h;
     CUtensorMap map;
     a.use_tma = (win_w <= 256 && win_h <= 256 &&
@@ -411,8 +462,11 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     if (!a.use_tma) memset(&map, 0, sizeof(map));
     auto kern = bbme_exhaustive2_kernel<BS, PNORM, SPLIT>;
     ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
-    dim3 grid((a.C + nb - 1) / nb, a.R, n);
-    kern<<<grid, threads, smem, stream>>>(map, a, g);
+    a.strips_x = (a.C + nb - 1) / nb;
+    if ((long long)a.strips_x * a.R * n > 0x7FFFFFFFLL) return GME_OK;
+    a.strips = a.strips_x * a.R * n;
+    const int resident = 2 * kNumSMs;                            // two CTAs per SM (registers); each walks its share of strips
+    kern<<<min(a.strips, resident), threads, smem, stream>>>(map, a, g);
     note_launch();
     *handled = true;
     return check_launch("bbme_exhaustive2_kernel");

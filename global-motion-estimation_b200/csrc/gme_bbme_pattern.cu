@@ -761,22 +761,21 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
 // min over (cost << 4 | index) keys.  The SDSP reuses the registers of the last LDSP step.  Steps
 // whose neighbourhood leaves the staged window or on which the clamp of bbme.py:503-504 could act
 // use the candidate-at-a-time evaluator (BlockEval<2, 1>).
-// The walks have different lengths, so a static block -> thread assignment leaves half of every
-// warp idle (round 1: 15.5 of 32 lanes active, profiles/r01k).  Here the kernel is ONE flat loop in
-// which every lane advances ITS block by one LDSP step per iteration; a lane whose block has
-// converged finishes it (SDSP, store) and takes the next block of the tile from a per-CTA queue
-// (one shared-memory atomic per warp and iteration, lanes ranked by ballot), so lanes only idle in
-// the tail of the tile.  The per-plane channel sums that the first estimate needs are accumulated
-// here (see PatternArgs::sums).
+// Round 1 measured 15.5 of 32 lanes active here and blamed the different walk lengths; the instruction-level profile
+// (profiles/r02i) showed something else: the blocks on which the clamp acts -- one or two lanes of a quarter of all
+// warps -- dragged their warps through the ~900-instruction general evaluator.  A per-lane work queue (tried, r02i)
+// made it worse: its hand-over and finish code ran in every iteration with a few lanes.  What is built: the clamped
+// block columns (first, last two) are tiles of their own and the clamped block rows are whole warps (a warp is 32
+// consecutive blocks of a tile row), so border blocks only meet border blocks; they use a window-only evaluator, and
+// the general one (walks that leave the window) is out of line.  The per-plane channel sums that the first estimate
+// needs are accumulated here (see PatternArgs::sums).
 // ---------------------------------------------------------------------------------------
 template <int PNORM, int NT>
-__global__ void __launch_bounds__(NT, 4) bbme_diamond2_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
+__global__ void __launch_bounds__(NT, 3) bbme_diamond2_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
 {
     constexpr int BS = 2;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
-    __shared__ int next_block;
-    if (threadIdx.x == 0) next_block = 0;             // (stage_window synchronises the CTA before anyone reads it)
 
     const int plane = blockIdx.z;
     // Tile columns: when the frame is wide enough (a.edge_tiles, set by the launcher), the block columns on which the clamp
@@ -818,112 +817,91 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond2_kernel(const __grid_const
     const uint32_t *win = reinterpret_cast<const uint32_t *>(smem);
     const int win_pw = a.win_w / 4;
     const int lane = threadIdx.x & 31;
-    const int total = a.tby << shift;                            // queue entries: tby rows of 2^shift slots (slots >= tw are skipped)
+    const int total = a.tby << shift;                            // tby rows of 2^shift slots (slots >= tw are skipped)
     const int rows_left = a.R - tile_r;                          // block rows of the frame this tile can hold
 
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
     int sum0 = 0, sum1 = 0;
-    bool active = false;                                         // this lane is walking a block
-    int bi = 0, bj = 0, br = 0, bc = 0, mr = 0, mc = 0;
-    uint32_t anchor = 0;
-    for (;;) {
-        const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-        if (need) {                                              // hand the next blocks of the tile to the idle lanes
-            const int leader = __ffs(need) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&next_block, __popc(need));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (!active) {
-                const int b = base + __popc(need & ((1u << lane) - 1u));
-                if (b < total) {
-                    const int lr = b >> shift, lc = b & ((1 << shift) - 1);
-                    if (lr < rows_left && lc < tw) {
-                        bi = tile_r + lr;
-                        bj = tile_c + lc;
-                        br = bi * BS;
-                        bc = bj * BS;
-                        const uint8_t *p = prev_plane + (unsigned)(br * (int)a.pitch + bc);   // 2-byte aligned: even column, pitch % 4 == 0
-                        anchor = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p)) |
-                                 ((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p + a.pitch)) << 16);
-                        e.anchor[0] = anchor & 0xFFFFu;
-                        e.anchor[1] = anchor >> 16;
-                        mr = br;
-                        mc = bc;
-                        active = true;
-                    }
-                }
-            }
-            if (base >= total && __ballot_sync(0xFFFFFFFFu, active) == 0) break;    // queue drained, nobody walking
-        }
-        if (!active) continue;
+    const WindowOnly<decltype(e)> w{e};
+    for (int b = threadIdx.x; b < total; b += NT) {              // a warp: 32 consecutive blocks of one tile row
+        const int lr = b >> shift, lc = b & ((1 << shift) - 1);
+        if (lr >= rows_left || lc >= tw) continue;
+        const int bi = tile_r + lr, bj = tile_c + lc;
+        const int br = bi * BS, bc = bj * BS;
+        const uint8_t *pa = prev_plane + (unsigned)(br * (int)a.pitch + bc);      // 2-byte aligned: even column, pitch % 4 == 0
+        const uint32_t anchor = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(pa)) |
+                                ((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(pa + a.pitch)) << 16);
+        e.anchor[0] = anchor & 0xFFFFu;
+        e.anchor[1] = anchor >> 16;
 
+        uint32_t z0[6], z1[6];                                   // row i: z0 = bytes 0..3, z1 = bytes 4..7 (byte 0 = column mc - 2)
         auto cost_of = [&](uint32_t px) -> uint32_t { return cost4_acc<PNORM>(px, anchor, 0u); };
-        int out_r, out_c;
-        bool done;
-        if (mr >= fr_lo && mr <= fr_hi && mc >= fc_lo && mc <= fc_hi) {      // one LDSP step, bbme.py:494-513
-            uint32_t z0[6], z1[6];                               // row i: z0 = bytes 0..3, z1 = bytes 4..7 (byte 0 = column mc - 2)
-            const int x = mc - 2 - wc0;
-            const uint32_t *p = win + (mr - 2 - wr0) * win_pw + (x >> 2);
-            const int sh = (x & 3) * 8;
+        int mr = br, mc = bc;
+        bool last_fast = false;
+        uint32_t centre_cost = 0;
+        for (;;) {                                               // LDSP, bbme.py:494-513
+            if (mr >= fr_lo && mr <= fr_hi && mc >= fc_lo && mc <= fc_hi) {
+                const int x = mc - 2 - wc0;
+                const uint32_t *p = win + (mr - 2 - wr0) * win_pw + (x >> 2);
+                const int sh = (x & 3) * 8;
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const uint32_t w0 = p[i * win_pw], w1 = p[i * win_pw + 1], w2 = p[i * win_pw + 2];
-                z0[i] = __funnelshift_r(w0, w1, sh);
-                z1[i] = __funnelshift_r(w1, w2, sh);
-            }
-            // candidate (dr, dc): rows dr+2, dr+3; bytes dc+2, dc+3 of each
-            uint32_t c[9];
-            c[0] = cost_of(__byte_perm(z0[2], z0[3], 0x7632));                                            // ( 0,  0)
-            c[1] = cost_of(__byte_perm(z0[4], z0[5], 0x7632));                                            // ( 2,  0)
-            c[2] = cost_of(__byte_perm(__funnelshift_r(z0[3], z1[3], 24), __funnelshift_r(z0[4], z1[4], 24), 0x5410));   // ( 1,  1)
-            c[3] = cost_of(__byte_perm(z1[2], z1[3], 0x5410));                                            // ( 0,  2)
-            c[4] = cost_of(__byte_perm(__funnelshift_r(z0[1], z1[1], 24), __funnelshift_r(z0[2], z1[2], 24), 0x5410));   // (-1,  1)
-            c[5] = cost_of(__byte_perm(z0[0], z0[1], 0x7632));                                            // (-2,  0)
-            c[6] = cost_of(__byte_perm(z0[1], z0[2], 0x6521));                                            // (-1, -1)
-            c[7] = cost_of(__byte_perm(z0[2], z0[3], 0x5410));                                            // ( 0, -2)
-            c[8] = cost_of(__byte_perm(z0[3], z0[4], 0x6521));                                            // ( 1, -1)
-            uint32_t key = c[0] << 4;                            // first strict minimum in candidate order; costs < 2^18
+                for (int i = 0; i < 6; i++) {
+                    const uint32_t w0 = p[i * win_pw], w1 = p[i * win_pw + 1], w2 = p[i * win_pw + 2];
+                    z0[i] = __funnelshift_r(w0, w1, sh);
+                    z1[i] = __funnelshift_r(w1, w2, sh);
+                }
+                // candidate (dr, dc): rows dr+2, dr+3; bytes dc+2, dc+3 of each
+                uint32_t c[9];
+                c[0] = cost_of(__byte_perm(z0[2], z0[3], 0x7632));                                            // ( 0,  0)
+                c[1] = cost_of(__byte_perm(z0[4], z0[5], 0x7632));                                            // ( 2,  0)
+                c[2] = cost_of(__byte_perm(__funnelshift_r(z0[3], z1[3], 24), __funnelshift_r(z0[4], z1[4], 24), 0x5410));   // ( 1,  1)
+                c[3] = cost_of(__byte_perm(z1[2], z1[3], 0x5410));                                            // ( 0,  2)
+                c[4] = cost_of(__byte_perm(__funnelshift_r(z0[1], z1[1], 24), __funnelshift_r(z0[2], z1[2], 24), 0x5410));   // (-1,  1)
+                c[5] = cost_of(__byte_perm(z0[0], z0[1], 0x7632));                                            // (-2,  0)
+                c[6] = cost_of(__byte_perm(z0[1], z0[2], 0x6521));                                            // (-1, -1)
+                c[7] = cost_of(__byte_perm(z0[2], z0[3], 0x5410));                                            // ( 0, -2)
+                c[8] = cost_of(__byte_perm(z0[3], z0[4], 0x6521));                                            // ( 1, -1)
+                uint32_t key = c[0] << 4;                        // first strict minimum in candidate order; costs < 2^18
 #pragma unroll
-            for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
-            const int kb = (int)(key & 15u);
-            done = kb == 0;
-            if (done) {                                          // SDSP on the registers of this step, bbme.py:515-529
-                uint32_t ks = c[0] << 4;
-                ks = min(ks, (cost_of(__byte_perm(__funnelshift_r(z0[2], z1[2], 24), __funnelshift_r(z0[3], z1[3], 24), 0x5410)) << 4) | 1u);   // (0, +1)
-                ks = min(ks, (cost_of(__byte_perm(z0[3], z0[4], 0x7632)) << 4) | 2u);                     // (+1, 0)
-                ks = min(ks, (cost_of(__byte_perm(z0[2], z0[3], 0x6521)) << 4) | 3u);                     // (0, -1)
-                ks = min(ks, (cost_of(__byte_perm(z0[1], z0[2], 0x7632)) << 4) | 4u);                     // (-1, 0)
-                const int k = (int)(ks & 15u);
-                out_r = mr + (int)((SRP >> (4 * k)) & 15) - 2;
-                out_c = mc + (int)((SCP >> (4 * k)) & 15) - 2;
-            } else {
+                for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
+                const int kb = (int)(key & 15u);
+                if (kb == 0) { last_fast = true; centre_cost = c[0]; break; }
                 mr += (int)((LRP >> (4 * kb)) & 15) - 2;
                 mc += (int)((LCP >> (4 * kb)) & 15) - 2;
+            } else if (mr >= wr0 + 2 && mr <= wr0 + a.win_h - 4 && mc >= wc0 + 2 && mc <= wc0 + 2 + a.win_w - 12) {
+                // frame-border block: the clamp acts, but every clamped candidate is in the staged window
+                if (ldsp_step_clamped(w, rmax, cmax, mr, mc)) { last_fast = false; break; }
+            } else {
+                const int2 to = ldsp_step_cold(e, rmax, cmax, mr, mc);
+                const bool stop = to.x == mr && to.y == mc;
+                mr = to.x;
+                mc = to.y;
+                if (stop) { last_fast = false; break; }
             }
+        }
+        int out_r, out_c;
+        if (last_fast) {                                         // SDSP on the registers of the last step, bbme.py:515-529
+            uint32_t key = centre_cost << 4;
+            key = min(key, (cost_of(__byte_perm(__funnelshift_r(z0[2], z1[2], 24), __funnelshift_r(z0[3], z1[3], 24), 0x5410)) << 4) | 1u);   // (0, +1)
+            key = min(key, (cost_of(__byte_perm(z0[3], z0[4], 0x7632)) << 4) | 2u);                           // (+1, 0)
+            key = min(key, (cost_of(__byte_perm(z0[2], z0[3], 0x6521)) << 4) | 3u);                           // (0, -1)
+            key = min(key, (cost_of(__byte_perm(z0[1], z0[2], 0x7632)) << 4) | 4u);                           // (-1, 0)
+            const int ks = (int)(key & 15u);
+            out_r = mr + (int)((SRP >> (4 * ks)) & 15) - 2;
+            out_c = mc + (int)((SCP >> (4 * ks)) & 15) - 2;
         } else if (mr >= wr0 + 2 && mr <= wr0 + a.win_h - 4 && mc >= wc0 + 2 && mc <= wc0 + 2 + a.win_w - 12) {
-            // frame-border block: the clamp acts, but every clamped candidate is in the staged window
-            const WindowOnly<decltype(e)> w{e};
-            done = ldsp_step_clamped(w, rmax, cmax, mr, mc);
-            if (done) sdsp_clamped(w, rmax, cmax, mr, mc, out_r, out_c);
+            sdsp_clamped(w, rmax, cmax, mr, mc, out_r, out_c);
         } else {
-            const int2 to = ldsp_step_cold(e, rmax, cmax, mr, mc);
-            done = to.x == mr && to.y == mc;
-            mr = to.x;
-            mc = to.y;
-            if (done) {
-                const int2 o = sdsp_cold(e, rmax, cmax, mr, mc);
-                out_r = o.x;
-                out_c = o.y;
-            }
+            const int2 o = sdsp_cold(e, rmax, cmax, mr, mc);
+            out_r = o.x;
+            out_c = o.y;
         }
-        if (done) {
-            const int o0 = out_c - bc, o1 = out_r - br;          // bbme.py:531-532
-            *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(o0, o1);
-            sum0 += o0;
-            sum1 += o1;
-            active = false;
-        }
+        const int o0 = out_c - bc, o1 = out_r - br;              // bbme.py:531-532
+        *reinterpret_cast<int2 *>(field + ((size_t)bi * a.C + bj) * 2) = make_int2(o0, o1);
+        sum0 += o0;
+        sum1 += o1;
     }
+    __syncwarp();
     if (a.sums) {
         sum0 = __reduce_add_sync(0xFFFFFFFFu, sum0);
         sum1 = __reduce_add_sync(0xFFFFFFFFu, sum1);
@@ -1054,7 +1032,7 @@ template <int PNORM>
 static int launch_diamond2(PatternArgs a, int n, cudaStream_t stream)
 {
     constexpr int NT = 256, BS = 2;
-    // 2048 blocks per CTA: the queue keeps the lanes busy until the tail of the tile, so the tile is large
+    // 2048 blocks per CTA, eight per thread
     const int tbx = 64, tby = min(32, a.R);              // (tbx is fixed in the kernel)
     const int margin = 12;
     const int edge_tiles = a.C >= 8 ? 1 : 0;             // the clamped block columns (first, last two) as tiles of their own

@@ -143,6 +143,30 @@ __device__ bool inverse3(const double (&A)[3][3], double (&inv)[3][3])
     return true;
 }
 
+// Exact warp-wide sum of an int64 per lane with three REDUX.SUM instead of five 64-bit shuffle steps: the two's-
+// complement bit pattern is cut into limbs of 22, 22 and 20 bits, each limb summed over the 32 lanes (< 2^27), and
+// the limb sums recombined modulo 2^64 -- exact whenever the true sum fits an int64, which the callers guarantee.
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+    const unsigned long long u = (unsigned long long)v;
+    const unsigned long long s0 = __reduce_add_sync(0xFFFFFFFFu, (unsigned)(u & 0x3FFFFFu));
+    const unsigned long long s1 = __reduce_add_sync(0xFFFFFFFFu, (unsigned)((u >> 22) & 0x3FFFFFu));
+    const unsigned long long s2 = __reduce_add_sync(0xFFFFFFFFu, (unsigned)(u >> 44));
+    return (long long)(s0 + (s1 << 22) + (s2 << 44));
+}
+
+// (row, column) of the field elements tid, tid + step, tid + 2 step, ... without a division per element
+struct RowCol {
+    int row, col, qs, rs, C;
+    __device__ __forceinline__ RowCol(int first, int step, int C_) : row(first / C_), col(first % C_), qs(step / C_), rs(step % C_), C(C_) {}
+    __device__ __forceinline__ void next()
+    {
+        row += qs;
+        col += rs;
+        if (col >= C) { col -= C; ++row; }
+    }
+};
+
 // One CTA of kFitBig threads per frame pair.  The field is KB-scale, so the kernel is latency-bound: the
 // distances are computed once (float64 model vector per block) and kept in shared memory for the radix
 // select and the masked sums; every block-wide step is a warp-shuffle reduction or scan.
@@ -198,6 +222,7 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
             unsigned int prefix = 0;                                   // bits of the answer found so far
             unsigned int dmax = 0;
             // the field is read with four independent loads in flight per thread: the kernel is latency-bound
+            RowCol rc(tid, kFitBig, L.C);
             for (int base = tid; base < N; base += 4 * kFitBig) {
                 int2 g[4];
 #pragma unroll
@@ -206,11 +231,11 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
                     g[u] = i < N ? __ldg(reinterpret_cast<const int2 *>(gt + 2 * i)) : make_int2(0, 0);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 4; u++, rc.next()) {
                     const int i = base + u * kFitBig;
                     if (i < N) {
                         int m0, m1;
-                        model_vector(p, i / L.C, i % L.C, m0, m1);
+                        model_vector(p, rc.row, rc.col, m0, m1);
                         const unsigned int d = (unsigned int)(abs(g[u].x - m0) + abs(g[u].y - m1));
                         if (cached) diff_cache[i] = d;
                         dmax = max(dmax, d);
@@ -268,9 +293,10 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
             }
             thr = prefix;
         } else if (L.model_field) {
-            for (int i = tid; i < N; i += kFitBig) {
+            RowCol rc(tid, kFitBig, L.C);
+            for (int i = tid; i < N; i += kFitBig, rc.next()) {
                 int m0, m1;
-                model_vector(p, i / L.C, i % L.C, m0, m1);
+                model_vector(p, rc.row, rc.col, m0, m1);
                 *reinterpret_cast<short2 *>(L.model_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
             }
         }
@@ -279,6 +305,7 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
         long long S[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) S[k] = 0;
+        RowCol rcs(tid, kFitBig, L.C);
         for (int base = tid; base < N; base += 4 * kFitBig) {
             int2 g[4];
 #pragma unroll
@@ -287,13 +314,13 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
                 g[u] = i < N ? __ldg(reinterpret_cast<const int2 *>(gt + 2 * i)) : make_int2(0, 0);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 4; u++, rcs.next()) {
                 const int i = base + u * kFitBig;
                 if (i < N) {
                     const bool out = a.robust ? (diff_of(i) > thr) : false;   // strict '>' (motion.py:244)
                     if (L.outlier) L.outlier[(size_t)pair * N + i] = out ? 1 : 0;
                     if (!out) {
-                        const long long x = 4 * (i / L.C), y = 4 * (i % L.C);  // motion.py:254-255 (32-bit division)
+                        const long long x = 4 * rcs.row, y = 4 * rcs.col;      // motion.py:254-255: x = 4 i, y = 4 j
                         S[0] += 1;         S[1] += x;             S[2] += y;
                         S[3] += x * x;     S[4] += x * y;         S[5] += y * y;
                         S[6] += g[u].x;    S[7] += x * g[u].x;    S[8] += y * g[u].x;
@@ -304,19 +331,13 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
         }
 #pragma unroll
         for (int k = 0; k < 12; k++) {
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) S[k] += __shfl_xor_sync(0xFFFFFFFFu, S[k], o);
+            S[k] = warp_sum_ll(S[k]);
             if (lane == 0) red[warp][k] = S[k];
         }
         __syncthreads();
         if (warp == 0) {
 #pragma unroll
-            for (int k = 0; k < 12; k++) {
-                long long v = red[lane][k];
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                S[k] = v;
-            }
+            for (int k = 0; k < 12; k++) S[k] = warp_sum_ll(red[lane][k]);
         }
 
         if (tid == 0) {
@@ -348,9 +369,10 @@ __global__ void __launch_bounds__(kFitBig) affine_fit_kernel(FitArgs a)
     if (a.final_field) {                       // motion.get_motion_field_affine with the final parameters (results.py:52-54)
         const FitLevel L = a.lv[a.nlevels - 1];
         const int N = L.R * L.C;
-        for (int i = tid; i < N; i += kFitBig) {
+        RowCol rc(tid, kFitBig, L.C);
+        for (int i = tid; i < N; i += kFitBig, rc.next()) {
             int m0, m1;
-            model_vector(p, i / L.C, i % L.C, m0, m1);
+            model_vector(p, rc.row, rc.col, m0, m1);
             *reinterpret_cast<short2 *>(a.final_field + ((size_t)pair * N + i) * 2) = make_short2((short)m0, (short)m1);
         }
     }
