@@ -195,7 +195,7 @@ struct Exhaustive2Geom {
     unsigned cpitch_rcp;   // ceil(2^32 / cpitch): i / cpitch == umulhi(i, cpitch_rcp) for i < 2^32 / cpitch
 };
 
-template <int BS, int PNORM, int SPLIT>
+template <int BS, int PNORM, int SPLIT, bool PERSIST>
 __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_constant__ CUtensorMap cur_map,
                                                                   ExhaustiveArgs a, Exhaustive2Geom g)
 {
@@ -268,8 +268,9 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
         store_anchors(anchors2, v);
     }
 
-    for (int it = 0, t = blockIdx.x; t < a.strips; ++it, t += gridDim.x) {
-    const int buf = it & 1;
+    // (PERSIST = false: one strip per CTA, the loop body runs once and all the prefetch code folds away)
+    for (int it = 0, t = blockIdx.x; PERSIST ? t < a.strips : it == 0; ++it, t += gridDim.x) {
+    const int buf = PERSIST ? (it & 1) : 0;
     int plane, bi, bj0;
     strip_origin(t, plane, bi, bj0);
     const int br = bi * BS, bc0 = bj0 * BS;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
     // ---- stage: raw window (TMA, already in flight; the next strip's is issued now), anchor blocks, result keys ----
     if (a.use_tma) {
         // raw[buf ^ 1] was last read by the copy expansion of the previous strip, which every thread has left
-        if (threadIdx.x == 0 && t + (int)gridDim.x < a.strips) issue_window(t + gridDim.x, buf ^ 1);
+        if (PERSIST && threadIdx.x == 0 && t + (int)gridDim.x < a.strips) issue_window(t + gridDim.x, buf ^ 1);
     } else {
         for (int i = threadIdx.x; i < g.rawpw * a.win_h; i += NT) {
             const int rr = wr0 + i / g.rawpw, cc = wc0 + (i % g.rawpw) * 4;
@@ -299,12 +300,12 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
     // anchor blocks: this strip's are in anchors2[buf] already (fetched while the previous strip was searched); the next
     // strip's are requested now and stored after the search, so their global-memory latency never shows
     uint32_t *anchors = anchors2 + buf * nanc;
-    const bool has_next = t + (int)gridDim.x < a.strips;
+    const bool has_next = PERSIST && t + (int)gridDim.x < a.strips;
     uint32_t next_anc[KA];
     if (has_next) fetch_anchors(t + gridDim.x, next_anc);
     for (int i = threadIdx.x; i < a.nb; i += NT) keys[i] = ~0ull;
     __syncthreads();
-    if (a.use_tma) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+    if (a.use_tma) mbar_wait(&bar[buf], PERSIST ? (uint32_t)((it >> 1) & 1) : 0u);
 
     // ---- four byte-shifted copies of the window ----------------------------------------------------------------
     // (flat index over rows x words; the row comes from a multiply-high with the host's reciprocal of cpitch, exact
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(384, 2) bbme_exhaustive2_kernel(const __grid_c
         }
     }
     if (has_next) store_anchors(anchors2 + (buf ^ 1) * nanc, next_anc);
-    __syncthreads();               // keys and copies are rewritten by the next strip, which also reads the new anchors
+    if (PERSIST) __syncthreads();  // keys and copies are rewritten by the next strip, which also reads the new anchors
     }   // strips
 }
 
@@ -442,8 +443,7 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     if (ncand > 256) return GME_OK;                              // key packs the row index in 8 bits
     Exhaustive2Geom g;
     g.tpb = min(ncand, 384 / SPLIT);
-    int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
-    nb = (a.C + (a.C + nb - 1) / nb - 1) / ((a.C + nb - 1) / nb);   // same number of strips per block row, evenly filled
+    const int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
     const int threads = (nb * g.tpb * SPLIT + 31) / 32 * 32;
     const int win_h = 2 * a.sw + 2 * BS - 1;
     int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4 + 15;  // +15: the first column is rounded down to 16 bytes
@@ -460,13 +460,24 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     a.use_tma = (win_w <= 256 && win_h <= 256 &&
                  make_plane_tensor_map(&map, a.cur, n, a.H, a.W, a.pitch, a.cur_stride, win_w, win_h)) ? 1 : 0;
     if (!a.use_tma) memset(&map, 0, sizeof(map));
-    auto kern = bbme_exhaustive2_kernel<BS, PNORM, SPLIT>;
-    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+
     a.strips_x = (a.C + nb - 1) / nb;
     if ((long long)a.strips_x * a.R * n > 0x7FFFFFFFLL) return GME_OK;
     a.strips = a.strips_x * a.R * n;
-    const int resident = 2 * kNumSMs;                            // two CTAs per SM (registers); each walks its share of strips
-    kern<<<min(a.strips, resident), threads, smem, stream>>>(map, a, g);
+    // Long strips (config 5: 87 window rows x 64 packed updates per thread): two persistent CTAs per SM, each walking its
+    // share of the strips with the next window and anchors prefetched.  Short strips (config 1: 47 rows x 36 updates,
+    // ~2 us): one strip per CTA -- measured 8 % faster there; the hardware's CTA scheduler balances the uneven border
+    // strips, which a static walk does not.
+    const long work = (long)(ncand + BS / SPLIT - 1) * (BS / SPLIT) * WPR * (PNORM == GME_PNORM_MSE ? 2 : 1);
+    if (work >= 3000 && a.strips > 2 * kNumSMs) {
+        auto kern = bbme_exhaustive2_kernel<BS, PNORM, SPLIT, true>;
+        ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+        kern<<<2 * kNumSMs, threads, smem, stream>>>(map, a, g);
+    } else {
+        auto kern = bbme_exhaustive2_kernel<BS, PNORM, SPLIT, false>;
+        ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+        kern<<<a.strips, threads, smem, stream>>>(map, a, g);
+    }
     note_launch();
     *handled = true;
     return check_launch("bbme_exhaustive2_kernel");

@@ -1,0 +1,6 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -x -q > gpurun_out/r2s_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2s_pytest.log
+tail -4 gpurun_out/r2s_pytest.log
+timeout 300 python tools/exh_bench.py > gpurun_out/r2s_exh.json 2>> gpurun_out/r2s_exh.err; cut -c150-800 gpurun_out/r2s_exh.json
