@@ -324,9 +324,12 @@ def main():
         frames = (S.pan_sequence(nf, H, W, step=(2, 1), seed=3) if motion == "pan"
                   else S.zoom_rotate_sequence(nf, H, W, seed=4) if motion == "zoomrot"
                   else S.affine_sequence(nf, H, W, seed=5))
-        per_step = max(2 * cores, 8)
-        for _ in range(args.warmup):
-            cpu_pairs_per_s(frames, procedure, window, cores, cores)
+        rate = 0.0
+        for _ in range(max(1, args.warmup)):
+            rate, _ = cpu_pairs_per_s(frames, procedure, window, cores, cores)
+        # a step = about one second of CPU work (a bounded sample of the workload), at least one pair per core and at
+        # most 16: long enough that thread start-up and the last-thread tail do not understate the reference
+        per_step = int(min(16 * cores, max(cores, round(rate / cores) * cores)))
         t = 0.0
         for _ in range(args.steps):
             _, dt = cpu_pairs_per_s(frames, procedure, window, per_step, cores)
@@ -524,9 +527,13 @@ def main():
         stages[name] = {"ms_per_step": per_call, "share": ms / max(sum(stage_ms), 1e-12), "algorithmic_gbs": gbs,
                         "frac_of_hbm_peak": gbs / hbm_peak}
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
-    traffic = None
+    traffic, ncu_dom = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        traffic = tj.get(dom)
+        det = tj.get("_detail", {}).get(dom, {})
+        ncu_dom = {k: det[k] for k in ("issue_active", "alu_pipe_pct", "fma_pipe_pct", "lsu_wavefronts_pct", "warp_instructions")
+                   if k in det} or None
     except Exception:
         pass
     kernel_names = {"pyramids": "pyr_down_kernel", "bbme_dense_l0": "bbme_diamond2_kernel",
@@ -536,6 +543,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "kernel_name": kernel_names[dom], "achieved": stages[dom]["algorithmic_gbs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": stages[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_ps[dom],
+                # what actually bounds the kernel (ncu of one warm step, profiles/traffic.json): share of issue slots used
+                # and pipe utilisation -- the pattern searches are instruction-issue bound, not HBM bound
+                "ncu": ncu_dom,
                 "whole_step_algorithmic_gbs": sum(bytes_ps.values()) / (ms_total / args.steps * 1e-3) / 1e9}
     exhaustive = None
     try:

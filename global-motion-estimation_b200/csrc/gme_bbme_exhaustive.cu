@@ -443,7 +443,12 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     if (ncand > 256) return GME_OK;                              // key packs the row index in 8 bits
     Exhaustive2Geom g;
     g.tpb = min(ncand, 384 / SPLIT);
-    const int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
+    // work of one thread for one column offset (packed updates); strips below ~3000 are "short": a CTA lives ~2 us and
+    // half of that is launch, TMA latency and drain
+    const long work = (long)(ncand + BS / SPLIT - 1) * (BS / SPLIT) * WPR * (PNORM == GME_PNORM_MSE ? 2 : 1);
+    if (work < 3000 && (ncand + 1) / 2 >= BS) g.tpb = (ncand + 1) / 2;     // short strips: two column offsets per thread,
+    int nb = max(1, min(384 / SPLIT / g.tpb, a.C));                        // so that a CTA holds more macroblocks
+    nb = max(1, min(nb, (256 - 19 - (2 * a.sw + 2 * BS - 1)) / BS + 1));   // the window must fit one TMA box (256 bytes wide)
     const int threads = (nb * g.tpb * SPLIT + 31) / 32 * 32;
     const int win_h = 2 * a.sw + 2 * BS - 1;
     int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4 + 15;  // +15: the first column is rounded down to 16 bytes
@@ -468,7 +473,6 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     // share of the strips with the next window and anchors prefetched.  Short strips (config 1: 47 rows x 36 updates,
     // ~2 us): one strip per CTA -- measured 8 % faster there; the hardware's CTA scheduler balances the uneven border
     // strips, which a static walk does not.
-    const long work = (long)(ncand + BS / SPLIT - 1) * (BS / SPLIT) * WPR * (PNORM == GME_PNORM_MSE ? 2 : 1);
     if (work >= 3000 && a.strips > 2 * kNumSMs) {
         auto kern = bbme_exhaustive2_kernel<BS, PNORM, SPLIT, true>;
         ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);

@@ -30,8 +30,10 @@ def parse(path):
         v = float(r[i_val].replace(",", ""))
         if r[i_metric].startswith("dram__bytes"):
             d[r[i_metric]] = v * UNIT[r[i_unit]]
-        else:
+        elif r[i_metric].startswith("gpu__time"):
             d[r[i_metric]] = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[i_unit], 1.0)
+        else:
+            d[r[i_metric]] = v
     return [launches[k] for k in sorted(launches)]
 
 
@@ -48,6 +50,18 @@ def main(paths):
             d["dram_bytes"] += l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0)
             d["us_under_ncu"] += l.get("gpu__time_duration.sum", 0.0)
             d["kernels"].append(l["kernel"].split("(")[0])
+            # what bounds the kernel: issue-slot utilisation and pipe utilisation of its longest launch
+            if l.get("gpu__time_duration.sum", 0.0) >= d.get("_longest", 0.0):
+                d["_longest"] = l.get("gpu__time_duration.sum", 0.0)
+                for key, name in (("smsp__issue_active.avg.per_cycle_active", "issue_active"),
+                                  ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pipe_pct"),
+                                  ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pipe_pct"),
+                                  ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu_wavefronts_pct"),
+                                  ("smsp__inst_executed.sum", "warp_instructions")):
+                    if key in l:
+                        d[name] = l[key]
+        for v in per.values():
+            v.pop("_longest", None)
         out[workload] = {k: int(v["dram_bytes"]) for k, v in per.items()}
         out[workload]["_detail"] = per
     json.dump(out, sys.stdout, indent=1)
