@@ -446,9 +446,9 @@ static int launch_fast2(ExhaustiveArgs a, int n, cudaStream_t stream, bool *hand
     // work of one thread for one column offset (packed updates); strips below ~3000 are "short": a CTA lives ~2 us and
     // half of that is launch, TMA latency and drain
     const long work = (long)(ncand + BS / SPLIT - 1) * (BS / SPLIT) * WPR * (PNORM == GME_PNORM_MSE ? 2 : 1);
-    if (work < 3000 && (ncand + 1) / 2 >= BS) g.tpb = (ncand + 1) / 2;     // short strips: two column offsets per thread,
-    int nb = max(1, min(384 / SPLIT / g.tpb, a.C));                        // so that a CTA holds more macroblocks
-    nb = max(1, min(nb, (256 - 19 - (2 * a.sw + 2 * BS - 1)) / BS + 1));   // the window must fit one TMA box (256 bytes wide)
+    // (tried for short strips: two column offsets per thread so that a CTA holds more macroblocks -- 0.50 vs 0.53 of
+    // the pipe ceiling on config 1; and evenly filled strips, nb = 9 instead of 10 there -- 0.49)
+    const int nb = max(1, min(384 / SPLIT / g.tpb, a.C));
     const int threads = (nb * g.tpb * SPLIT + 31) / 32 * 32;
     const int win_h = 2 * a.sw + 2 * BS - 1;
     int win_w = 2 * a.sw + 2 * BS - 1 + (nb - 1) * BS + 4 + 15;  // +15: the first column is rounded down to 16 bytes

@@ -601,9 +601,13 @@ __device__ __forceinline__ bool d16_update(uint32_t (&c)[9], int &mr, int &mc, u
                                            uint32_t a0, uint32_t a1)
 {
     if constexpr (KB != 0) {
+        // the previous centre was a fast-path one, so only the bounds the move runs towards can be crossed
         mr += ldsp_r(KB);
         mc += ldsp_c(KB);
-        if (!f.ok(mr, mc)) return false;
+        if (ldsp_r(KB) > 0 && mr > f.r_hi) return false;
+        if (ldsp_r(KB) < 0 && mr < f.r_lo) return false;
+        if (ldsp_c(KB) > 0 && mc > f.c_hi) return false;
+        if (ldsp_c(KB) < 0 && mc < f.c_lo) return false;
         xb += (uint32_t)(ldsp_r(KB) * kD16Pitch + ldsp_c(KB));
     }
     const uint32_t n0 = d16_next<PNORM, KB, 0>(c, xb, a0, a1), n1 = d16_next<PNORM, KB, 1>(c, xb, a0, a1),

@@ -14,6 +14,10 @@
 // 16-bit pairs (two pixels per 32-bit lane op; row sums fit 12 bits and the 5x5 sum + 128
 // fits 16 bits, so the packed lanes never carry), and a rolling window of five row sums for
 // the vertical tap.  Output rows leave as 8-byte stores, 128 bytes per 16 threads.
+// (Round 2 tried persistent CTAs with two staging buffers, the next tile's cp.async in flight while the current one is
+// filtered: 72 us instead of 59 at 1080p -- two 37 KB buffers leave three CTAs per SM instead of six, and the lost
+// warps cost more than the hidden staging latency gains.  Fusing the second level into the first does not pay either:
+// the kernel is issue-bound, and the 2-pixel halo of the coarser level means recomputing 27 % of the finer one.)
 #include "gme_common.cuh"
 
 namespace gme {

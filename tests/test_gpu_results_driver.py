@@ -188,3 +188,26 @@ def test_frame_prefetcher_equals_get_video_frames(tmp_path):
             got.extend(f.numpy().copy() for f in frames)
             pf.release(slot)
         assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+def test_streaming_dump_equals_the_unchanged_driver_on_an_odd_geometry(tmp_path):
+    """A 250 x 330 clip (neither dimension a multiple of 16: padded pitch, partial last tiles, chunks that do not divide
+    the pair count): the streaming dump and the reference's unchanged results.py on top of the drop-in modules must
+    write the same bytes."""
+    import make_results_golden as G
+    import gme_results
+    import gme_synth as S
+    script = _staged("results.py")
+    seq = S.zoom_rotate_sequence(13, 250, 330, zoom_per_frame=0.004, deg_per_frame=0.3, seed=31)
+    os.makedirs(tmp_path / "resources" / "videos")
+    clip = str(tmp_path / "resources" / "videos" / "odd.mp4")
+    if not G.write_lossless_clip(clip, seq):
+        pytest.skip("no lossless (FFV1) video writer in this OpenCV build")
+    _run_driver(script, ["-v", "odd.mp4", "-f", "2"], str(tmp_path))
+    want = G.digest_tree(str(tmp_path / "results" / "odd"))
+    out = str(tmp_path / "stream")
+    os.makedirs(out)
+    psnr = gme_results.dump_results(clip, os.path.join(out, ""), 2, chunk=4)
+    assert G.digest_tree(out) == want and len(want) == 5 * 11
+    with open(tmp_path / "results" / "odd" / "psnr_records.json") as f:
+        assert json.load(f) == psnr

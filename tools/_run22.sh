@@ -1,0 +1,8 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2v_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2v_pytest.log
+tail -4 gpurun_out/r2v_pytest.log
+timeout 300 python tools/stage_bench.py --tag bounds > gpurun_out/r2v_stage_new.json 2> gpurun_out/r2v_stage_new.err
+timeout 300 python tools/stage_bench.py --tag bounds_480 --workload gme_480p > gpurun_out/r2v_stage_480.json 2>> gpurun_out/r2v_stage_new.err
+cat gpurun_out/r2v_stage_*.json
