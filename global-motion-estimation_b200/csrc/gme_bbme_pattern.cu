@@ -13,6 +13,7 @@
 // Scan orders, strict '<' first-minimum tie-breaking, the diamond clamp to H-bs-1, the
 // swapped SDSP offsets, the double-counted three-step offset and the unbounded 2D-log walk
 // are reproduced exactly; the oracle is oracle/gme_oracle.c.
+#include <cstdlib>
 #include <cstring>
 
 #include "gme_common.cuh"
@@ -1037,7 +1038,8 @@ static int launch_diamond2(PatternArgs a, int n, cudaStream_t stream)
 {
     constexpr int NT = 256, BS = 2;
     // 2048 blocks per CTA, eight per thread
-    const int tbx = 64, tby = min(32, a.R);              // (tbx is fixed in the kernel)
+    static const int tby_env = getenv("GME_D2_TBY") ? atoi(getenv("GME_D2_TBY")) : 32;   // TEMPORARY (A/B on the box)
+    const int tbx = 64, tby = min(tby_env, a.R);         // (tbx is fixed in the kernel)
     const int margin = 12;
     const int edge_tiles = a.C >= 8 ? 1 : 0;             // the clamped block columns (first, last two) as tiles of their own
     a.edge_tiles = edge_tiles;
