@@ -13,7 +13,6 @@
 // Scan orders, strict '<' first-minimum tie-breaking, the diamond clamp to H-bs-1, the
 // swapped SDSP offsets, the double-counted three-step offset and the unbounded 2D-log walk
 // are reproduced exactly; the oracle is oracle/gme_oracle.c.
-#include <cstdlib>
 #include <cstring>
 
 #include "gme_common.cuh"
@@ -1037,9 +1036,8 @@ template <int PNORM>
 static int launch_diamond2(PatternArgs a, int n, cudaStream_t stream)
 {
     constexpr int NT = 256, BS = 2;
-    // 2048 blocks per CTA, eight per thread
-    static const int tby_env = getenv("GME_D2_TBY") ? atoi(getenv("GME_D2_TBY")) : 32;   // TEMPORARY (A/B on the box)
-    const int tbx = 64, tby = min(tby_env, a.R);         // (tbx is fixed in the kernel)
+    // 1024 blocks per CTA, four per thread
+    const int tbx = 64, tby = min(16, a.R);              // (tbx is fixed in the kernel; 16 rows measured best of 4..32)
     const int margin = 12;
     const int edge_tiles = a.C >= 8 ? 1 : 0;             // the clamped block columns (first, last two) as tiles of their own
     a.edge_tiles = edge_tiles;
@@ -1070,7 +1068,11 @@ static int launch_pattern_pn(PatternArgs a, int n, int bs, cudaStream_t stream)
     case 4: return launch_fast<4, 1, PNORM>(a, n, stream);
     case 8: return launch_fast<8, 4, PNORM>(a, n, stream);
     case 12: return launch_fast<12, 4, PNORM>(a, n, stream);
-    case 16: return launch_fast<16, 16, PNORM>(a, n, stream);    // (a warp per macroblock, G = 32, measured 2-10 % slower)
+    // (three-step / 2D-log with a warp per macroblock: G = 32 in this kernel measured 2-10 % slower in round 1; a
+    //  dedicated kernel on the diamond kernel's skeleton -- queue, 240-byte pitch, window-only evaluator, general one
+    //  out of line -- 24 % slower in round 2, 731 vs 588 us at 1080p: these walks are dominated by per-candidate
+    //  steering that is uniform across the lanes, and two macroblocks per warp halve it per macroblock)
+    case 16: return launch_fast<16, 16, PNORM>(a, n, stream);
     default: break;
     }
     if (a.sums) return GME_ERR_UNSUPPORTED;              // channel sums are only produced by the tiled kernel
