@@ -579,6 +579,42 @@ __device__ __forceinline__ uint32_t d16_cand(uint32_t xb, uint32_t a0, uint32_t 
     return __reduce_add_sync(0xFFFFFFFFu, acc) << 4;
 }
 
+// The same for a centre whose column is word-aligned in the window (every fresh walk: macroblock columns and the
+// window origin are multiples of 16): the word offset and the shift of a column offset are compile-time constants,
+// and the three candidates in the centre's own column need no second word and no shift.
+template <int PNORM, int DR, int DC>
+__device__ __forceinline__ uint32_t d16_cand_aligned(uint32_t xb, uint32_t a0, uint32_t a1)
+{
+    constexpr int wofs = DC < 0 ? -4 : 0;
+    constexpr int sh = ((DC + 4) & 3) * 8;
+    const uint32_t addr = xb + (uint32_t)(DR * kD16Pitch + wofs);
+    uint32_t v0, v1;
+    if constexpr (sh == 0) {
+        v0 = lds_u32(addr);
+        v1 = lds_u32(addr + 8 * kD16Pitch);
+    } else {
+        v0 = __funnelshift_r(lds_u32(addr), lds_u32(addr + 4), sh);
+        v1 = __funnelshift_r(lds_u32(addr + 8 * kD16Pitch), lds_u32(addr + 8 * kD16Pitch + 4), sh);
+    }
+    uint32_t acc = cost4_acc<PNORM>(v0, a0, 0u);
+    acc = cost4_acc<PNORM>(v1, a1, acc);
+    return __reduce_add_sync(0xFFFFFFFFu, acc) << 4;
+}
+
+template <int PNORM>
+__device__ __forceinline__ void d16_first_aligned(uint32_t (&c)[9], uint32_t xb, uint32_t a0, uint32_t a1)
+{
+    c[0] = d16_cand_aligned<PNORM, ldsp_r(0), ldsp_c(0)>(xb, a0, a1);
+    c[1] = d16_cand_aligned<PNORM, ldsp_r(1), ldsp_c(1)>(xb, a0, a1);
+    c[2] = d16_cand_aligned<PNORM, ldsp_r(2), ldsp_c(2)>(xb, a0, a1);
+    c[3] = d16_cand_aligned<PNORM, ldsp_r(3), ldsp_c(3)>(xb, a0, a1);
+    c[4] = d16_cand_aligned<PNORM, ldsp_r(4), ldsp_c(4)>(xb, a0, a1);
+    c[5] = d16_cand_aligned<PNORM, ldsp_r(5), ldsp_c(5)>(xb, a0, a1);
+    c[6] = d16_cand_aligned<PNORM, ldsp_r(6), ldsp_c(6)>(xb, a0, a1);
+    c[7] = d16_cand_aligned<PNORM, ldsp_r(7), ldsp_c(7)>(xb, a0, a1);
+    c[8] = d16_cand_aligned<PNORM, ldsp_r(8), ldsp_c(8)>(xb, a0, a1);
+}
+
 template <int PNORM, int KB, int J>
 __device__ __forceinline__ uint32_t d16_next(const uint32_t (&c)[9], uint32_t xb, uint32_t a0, uint32_t a1)
 {
@@ -724,7 +760,10 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
                     continue;
                 }
                 xb = lane_base + (uint32_t)((mr - wr0) * kD16Pitch + (mc - wc0));
-                d16_update<PNORM, 0>(c, mr, mc, xb, fast, a0, a1);
+                if (((mc - wc0) & 3) == 0)                         // (warp-uniform) every fresh walk starts here
+                    d16_first_aligned<PNORM>(c, xb, a0, a1);
+                else                                               // a restart after the border evaluator moved the centre
+                    d16_update<PNORM, 0>(c, mr, mc, xb, fast, a0, a1);
             } else if (!d16_ldsp<PNORM>(c, kb, mr, mc, xb, fast, a0, a1)) {
                 kb = 0;                                            // the move took the centre off the fast path
                 continue;
