@@ -34,6 +34,7 @@ struct PatternArgs {
     int win_w, win_h;  // staged window: win_w bytes per row (multiple of 16), win_h rows
     int use_tma;
     int edge_tiles;    // dense diamond kernel: the clamped block columns (first, last two) are tiles of their own
+    uint32_t key_scale;   // 16, as a run-time value (dense diamond kernel: keeps the key arithmetic off the ALU pipe)
     unsigned long long *sums;   // optional, [n][2]: per-plane sums of the two field channels (pipeline: the dense
                                 // first estimate, motion.py:186-188, is a mean -- no second pass over the field)
 };
@@ -477,6 +478,9 @@ __global__ void __launch_bounds__(NT, 3) bbme_pattern_kernel(const __grid_consta
 
     const int group = threadIdx.x / G, ngroups = NT / G;
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
+    // 16, but not a constant the compiler can turn back into a shift: the kernel is bound by the ALU pipe (shifts, byte
+    // permutes, VABSDIFF4, min), and `cost * k16 + j` is a multiply-add on the other one
+    const uint32_t k16 = a.key_scale;
     int sum0 = 0, sum1 = 0;
     for (int b = group; b < a.tbx * a.tby; b += ngroups) {
         const int bi = tile_r + b / a.tbx, bj = tile_c + b % a.tbx;
@@ -581,7 +585,10 @@ __device__ __forceinline__ uint32_t d16_cand(uint32_t xb, uint32_t a0, uint32_t 
 
 // The same for a centre whose column is word-aligned in the window (every fresh walk: macroblock columns and the
 // window origin are multiples of 16): the word offset and the shift of a column offset are compile-time constants,
-// and the three candidates in the centre's own column need no second word and no shift.
+// and the three candidates in the centre's own column need no second word and no shift.  (Measured: 351 -> 336 us on
+// the full-resolution level.  Extending it to the vertical moves, which keep the alignment, and to the SDSP gave
+// nothing more, 335.9 us, and was dropped.  The predicate must come from warp-uniform values such as mc - wc0: derived
+// from xb, which holds the lane offset, every warp reduction downstream got a divergent-warp fallback -- 2.2 x the code.)
 template <int PNORM, int DR, int DC>
 __device__ __forceinline__ uint32_t d16_cand_aligned(uint32_t xb, uint32_t a0, uint32_t a1)
 {
@@ -864,6 +871,9 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond2_kernel(const __grid_const
     const int rows_left = a.R - tile_r;                          // block rows of the frame this tile can hold
 
     int32_t *field = a.field + (size_t)plane * a.R * a.C * 2;
+    // 16, but not a constant the compiler can turn back into a shift: the kernel is bound by the ALU pipe (shifts, byte
+    // permutes, VABSDIFF4, min), and `cost * k16 + j` is a multiply-add on the other one
+    const uint32_t k16 = a.key_scale;
     int sum0 = 0, sum1 = 0;
     const WindowOnly<decltype(e)> w{e};
     for (int b = threadIdx.x; b < total; b += NT) {              // a warp: 32 consecutive blocks of one tile row
@@ -904,9 +914,9 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond2_kernel(const __grid_const
                 c[6] = cost_of(__byte_perm(z0[1], z0[2], 0x6521));                                            // (-1, -1)
                 c[7] = cost_of(__byte_perm(z0[2], z0[3], 0x5410));                                            // ( 0, -2)
                 c[8] = cost_of(__byte_perm(z0[3], z0[4], 0x6521));                                            // ( 1, -1)
-                uint32_t key = c[0] << 4;                        // first strict minimum in candidate order; costs < 2^18
+                uint32_t key = c[0] * k16;                       // first strict minimum in candidate order; costs < 2^18
 #pragma unroll
-                for (int j = 1; j < 9; j++) key = min(key, (c[j] << 4) | (uint32_t)j);
+                for (int j = 1; j < 9; j++) key = min(key, c[j] * k16 + (uint32_t)j);
                 const int kb = (int)(key & 15u);
                 if (kb == 0) { last_fast = true; centre_cost = c[0]; break; }
                 mr += (int)((LRP >> (4 * kb)) & 15) - 2;
@@ -924,11 +934,11 @@ __global__ void __launch_bounds__(NT, 3) bbme_diamond2_kernel(const __grid_const
         }
         int out_r, out_c;
         if (last_fast) {                                         // SDSP on the registers of the last step, bbme.py:515-529
-            uint32_t key = centre_cost << 4;
-            key = min(key, (cost_of(__byte_perm(__funnelshift_r(z0[2], z1[2], 24), __funnelshift_r(z0[3], z1[3], 24), 0x5410)) << 4) | 1u);   // (0, +1)
-            key = min(key, (cost_of(__byte_perm(z0[3], z0[4], 0x7632)) << 4) | 2u);                           // (+1, 0)
-            key = min(key, (cost_of(__byte_perm(z0[2], z0[3], 0x6521)) << 4) | 3u);                           // (0, -1)
-            key = min(key, (cost_of(__byte_perm(z0[1], z0[2], 0x7632)) << 4) | 4u);                           // (-1, 0)
+            uint32_t key = centre_cost * k16;
+            key = min(key, cost_of(__byte_perm(__funnelshift_r(z0[2], z1[2], 24), __funnelshift_r(z0[3], z1[3], 24), 0x5410)) * k16 + 1u);   // (0, +1)
+            key = min(key, cost_of(__byte_perm(z0[3], z0[4], 0x7632)) * k16 + 2u);                           // (+1, 0)
+            key = min(key, cost_of(__byte_perm(z0[2], z0[3], 0x6521)) * k16 + 3u);                           // (0, -1)
+            key = min(key, cost_of(__byte_perm(z0[1], z0[2], 0x7632)) * k16 + 4u);                           // (-1, 0)
             const int ks = (int)(key & 15u);
             out_r = mr + (int)((SRP >> (4 * ks)) & 15) - 2;
             out_c = mc + (int)((SCP >> (4 * ks)) & 15) - 2;
@@ -1135,6 +1145,7 @@ int launch_bbme_pattern(const uint8_t *prev, size_t prev_stride, const uint8_t *
     a.sw = sw; a.procedure = procedure;
     a.field = field;
     a.sums = sums;
+    a.key_scale = 16;
     if (a.R == 0 || a.C == 0 || n == 0) return GME_OK;
     return pnorm == GME_PNORM_MAE ? launch_pattern_pn<GME_PNORM_MAE>(a, n, bs, stream)
                                   : launch_pattern_pn<GME_PNORM_MSE>(a, n, bs, stream);
