@@ -17,7 +17,10 @@
 // (Round 2 tried persistent CTAs with two staging buffers, the next tile's cp.async in flight while the current one is
 // filtered: 72 us instead of 59 at 1080p -- two 37 KB buffers leave three CTAs per SM instead of six, and the lost
 // warps cost more than the hidden staging latency gains.  Fusing the second level into the first does not pay either:
-// the kernel is issue-bound, and the 2-pixel halo of the coarser level means recomputing 27 % of the finer one.)
+// the kernel is issue-bound, and the 2-pixel halo of the coarser level means recomputing 27 % of the finer one.
+// The two 32-bit loads of hrow are 4-way bank conflicts (every lane reads the same word of its 16-byte chunk; 44 % of
+// the kernel's shared wavefronts, ncu r02); taking those words from the neighbouring lanes with two shuffles instead
+// removed the conflicts and cost more than it saved -- 48 registers instead of 40, 63.6 us instead of 59.3.)
 #include "gme_common.cuh"
 
 namespace gme {
