@@ -332,7 +332,9 @@ class Pipeline:
         self.run(prev, cur, procedure, window, outlier_fraction)   # warm-up outside capture (module load, attributes)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: other threads of the process (a decode thread, NCCL's watchdog) may call the CUDA runtime
+        # while this one captures
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self.run(prev, cur, procedure, window, outlier_fraction)
         self.graph = g
         self._graph_key = (prev.ptr, cur.ptr, procedure, window, outlier_fraction)
@@ -443,7 +445,7 @@ class PairSession:
             self.pipe.run(prev, cur, *key)                                 # warm-up / validation outside capture
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self.pipe.run(prev, cur, *key)
                 self.out_dev[:6] = self.pipe.params[0]
                 self.out_dev[6] = self.pipe.status[0].to(torch.float64)
