@@ -819,6 +819,11 @@ __global__ void __launch_bounds__(NT, 4) bbme_diamond16_kernel(const __grid_cons
 // consecutive blocks of a tile row), so border blocks only meet border blocks; they use a window-only evaluator, and
 // the general one (walks that leave the window) is out of line.  The per-plane channel sums that the first estimate
 // needs are accumulated here (see PatternArgs::sums).
+// What remains is the walk-length divergence (17 of 32 lanes active on average).  Compacting the walks between steps
+// was built and measured (round 2): centre + anchor of every block in shared memory, rounds of 1..k LDSP steps, the
+// blocks still walking appended to the next round's list with one ballot and one shared atomic per warp, register-path
+// and clamped centres in separate lists.  Bit-identical, and slower: 81.7 us (k = 2) .. 88 us (k = 1) against 73 us --
+// the list/state indirection alone costs 12 us (k = 100, no re-queueing: 85 us), compaction wins back 4.
 // ---------------------------------------------------------------------------------------
 template <int PNORM, int NT>
 __global__ void __launch_bounds__(NT, 3) bbme_diamond2_kernel(const __grid_constant__ CUtensorMap cur_map, PatternArgs a)
