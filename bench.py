@@ -300,6 +300,8 @@ def main():
     ap.add_argument("--workload", default="gme_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="end", choices=["end", "step"],
+                    help="N > 1: one all-gather of every step's rows at the end of the timed region, or one per step")
     ap.add_argument("--lanes", type=int, default=2, help="sub-batches of one step on forked streams (Pipeline(lanes=...))")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="upload/compute chunks per step of the host-frames arm")
     args = ap.parse_args()
@@ -402,12 +404,16 @@ def main():
     host_frames.copy_(seq)
     del seq
     prev, cur = planes.view(0, pairs), planes.view(DISTANCE, nf)
-    # Two pipelines (workspace + outputs) alternate between steps when there is a gather: the kernels write the
-    # [pairs, 7] rows (6 affine parameters + squared-error sum) straight into pipe.rows, the all-gather of step k runs on
-    # NCCL's stream while step k + 1 computes into the other set, and a set is reused only after its gather is done.
-    # Each set runs as args.lanes sub-batches on forked streams (the other lane's block matching fills the holes the
+    # The kernels write the [pairs, 7] rows (6 affine parameters + squared-error sum) straight into pipe.rows.  On several
+    # GPUs the rows of every rank go to every rank -- the one exchange of the path (one collective at the end
+    # of the job).  --gather end (default): every step's rows are copied into a [steps, pairs, 7] device buffer and ONE
+    # all-gather closes the timed region.  --gather step: an all-gather per step.  Either way the copy / gather of step k
+    # runs on another stream while step k + 1 computes into a second pipeline (a set is reused only after its rows have
+    # been taken).
+    # Each pipeline runs as args.lanes sub-batches on forked streams (the other lane's block matching fills the holes the
     # small dependent fit kernels and every kernel's last wave leave) and is captured ONCE in a CUDA graph; a step is
     # one graph launch (Pipeline.capture / replay, the public API).
+    per_step_gather = world > 1 and args.gather == "step"
     pipes = [D.Pipeline(pairs, H, W, dev, lanes=args.lanes) for _ in range(2 if world > 1 else 1)]
     launches_before = N.launch_count()
     pipes[0].run(prev, cur, procedure, window)          # eager once: kernels per step, counted by the library
@@ -422,6 +428,20 @@ def main():
     gathered = [torch.empty((total_pairs, 7), dtype=torch.float64, device=dev) for _ in pipes]
     pending = [None for _ in pipes]
     turn = [0]
+    job_rows = job_gathered = None
+    if world > 1 and not per_step_gather:
+        job_rows = torch.zeros((args.steps, pairs, 7), dtype=torch.float64, device=dev)
+        job_gathered = torch.empty((world * args.steps * pairs, 7), dtype=torch.float64, device=dev)
+    done_steps = [0]
+    side_stream = torch.cuda.Stream(dev)
+
+    class RowsTaken:                                    # same protocol as the NCCL work handle: .wait() orders `main` after it
+        def __init__(self, main):
+            self.main, self.event = main, torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream())
+
+        def wait(self):
+            self.main.wait_event(self.event)
     flush = None if "inputs larger" in config["l2_policy"] else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     runner = D.HostSequenceRunner(nf, H, W, DISTANCE, chunk=max(1, -(-pairs // max(1, args.e2e_chunks))), procedure=procedure, window=window,
@@ -445,8 +465,22 @@ def main():
             pending[i].wait()                           # (stream-level) the gather that still reads this set's rows
             pending[i] = None
         pipes[i].replay()                               # results: .rows (.params / .sse) / .status / .comp on the device
-        if world > 1:                                   # the only exchange of the path: [pairs, 7] rows to every rank
+        if per_step_gather:
             pending[i] = GD.gather_rows_async(pipes[i].rows, gathered[i])
+        elif job_rows is not None:                      # 3.5 KB device copy on a side stream; the gather comes once, in finish()
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side_stream.wait_event(ready)
+            with torch.cuda.stream(side_stream):
+                job_rows[done_steps[0] % args.steps].copy_(pipes[i].rows)
+                pending[i] = RowsTaken(main)
+            done_steps[0] += 1
+
+    def finish(e2e):                                    # closes a timed region
+        drain()
+        if job_rows is not None and e2e is False:
+            dist.all_gather_into_tensor(job_gathered, job_rows.view(-1, 7))
 
     def drain():                                        # orders the current stream after every gather still in flight
         for i, w in enumerate(pending):
@@ -471,7 +505,7 @@ def main():
             start.record()
             for _ in range(steps):
                 step(e2e)
-            drain()                                     # the last gathers belong to the timed region
+            finish(e2e)                                 # the gather(s) belong to the timed region
             end.record()
             barrier()
         ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)
@@ -608,6 +642,8 @@ def main():
                 "h2d_gbs": runner.h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9},
         "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
         "launch": f"one CUDA graph per step: {pipes[0].lanes} lane(s) of gme_pipeline on forked streams ({launches_per_step} kernels)",
+        "exchange": (None if world == 1 else "one all_gather_into_tensor per step, overlapped with the next step" if per_step_gather
+                     else f"one all_gather_into_tensor of all {args.steps} steps' [pairs, 7] rows at the end of the timed region"),
         "stage_pass": {"ms_per_step": ms_stage_pass / args.steps, "lanes": 1, "launch": "eager, stages bracketed by CUDA events",
                        "note": "separate timed pass of the same steps; source of `stages` and of the roofline's kernel durations"},
         "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "bbme_exhaustive": exhaustive,
